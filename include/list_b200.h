@@ -1,0 +1,200 @@
+/*
+ * list_b200.h -- C ABI of the B200-native LIST per-query SDF hot path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its
+ * own -- its hot path is a sequence of ATen calls inside two nn.Modules -- so every
+ * entry point below cites the reference lines (relative to the reference repo root)
+ * whose work it replaces.  The Python mirror of the reference's module API
+ * (list_b200/network/{modules,models,executors}.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; all pointers are DEVICE pointers unless the
+ *    name ends in _host; `stream` is a cudaStream_t passed as void*.
+ *  - the caller owns every buffer (including workspaces); the library allocates
+ *    nothing, keeps no pointer after return, and never synchronises: all work is
+ *    enqueued on `stream`.
+ *  - return 0 on success, a negative errno-style code otherwise; the message is
+ *    available through list_b200_last_error() (thread-local).  Nothing throws.
+ *  - re-entrant: no global mutable state besides the thread-local error string
+ *    (nn.DataParallel replicas call from parallel host threads, reference
+ *    train.py:126).
+ *  - there is no CPU fallback and no other backend: sm_100a only.
+ */
+#ifndef LIST_B200_H
+#define LIST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define LIST_API __attribute__((visibility("default")))
+#else
+#define LIST_API
+#endif
+
+#define LIST_B200_ABI_VERSION 1
+#define LIST_MAX_LEVELS 8
+#define LIST_MAX_MAPS 8
+#define LIST_NUM_DISP 7          /* reference network/modules.py:205-212 */
+
+enum { LIST_F32 = 0, LIST_BF16 = 1 };
+
+enum {
+  LIST_OK = 0,
+  LIST_EINVAL = -22,             /* bad argument (shape, alignment, dtype) */
+  LIST_ENOMEM = -12,             /* caller-provided workspace too small    */
+  LIST_ECUDA = -5,               /* a CUDA call / launch failed            */
+  LIST_ENOSYS = -38              /* not supported on this device           */
+};
+
+/* Per-image tensors the hot path reads, in the kernel layouts (channels-last).
+ * Produced by list_prep_maps / list_prep_volume from the reference-layout tensors. */
+typedef struct ListCtx {
+  int32_t B;                     /* images                                                  */
+  int32_t dtype;                 /* LIST_F32 | LIST_BF16: storage type of maps and vols      */
+  int32_t map_size;              /* 137 (reference modules.py:16)                            */
+  int32_t map_channels;          /* 1024 = 64+64+128+256+512, order f1..f5 (modules.py:53)   */
+  const void* maps;              /* [B][map_size][map_size][map_channels]                    */
+  int32_t n_levels;              /* 6                                                        */
+  int32_t reserved0;
+  int32_t vol_res[LIST_MAX_LEVELS];   /* 128,128,64,32,16,8                                  */
+  int32_t vol_ch[LIST_MAX_LEVELS];    /* 1,16,32,64,128,128                                  */
+  const void* vols[LIST_MAX_LEVELS];  /* [B][R][R][R][C] (D,H,W,C)                           */
+  const float* trans_mat;        /* [B][4][3] fp32 (reference models.py:86)                  */
+} ListCtx;
+
+/* Column layout of one feature row X[n][0..k_pad) written by the gather kernels.
+ * The reference order is [vox(c*7+d) | percep | q] (modules.py:272-275); the kernels use
+ * [percep | level l, displacement d, channel c ... | scalar levels | q | zero pad] so that
+ * every segment is 16-byte aligned.  perm[new] = reference column. */
+typedef struct ListLayout {
+  int32_t k_out;                 /* 3610                                                     */
+  int32_t k_pad;                 /* k_out rounded up to 64 (3648)                            */
+  int32_t map_off;               /* first column of the 2-D features                         */
+  int32_t xyz_off;               /* first column of q                                        */
+  int32_t vol_off[LIST_MAX_LEVELS];   /* first column of level l; +d*C+c inside              */
+} ListLayout;
+
+/* Kernel-format copies of the implicit MLP (reference modules.py:196-200); masters stay
+ * nn.Parameters under the reference's state_dict keys in the Python wrapper. */
+typedef struct ListWeights {
+  int32_t dtype;                 /* LIST_F32 | LIST_BF16: type of w0,w1,w2                   */
+  int32_t k_pad;                 /* columns of w0 (ListLayout.k_pad), zero padded            */
+  int32_t n0, n1, n2;            /* 512, 256, 256                                            */
+  int32_t reserved0;
+  const void* w0;                /* [n0][k_pad]  fc_0, columns permuted by ListLayout        */
+  const void* w1;                /* [n1][n0]     fc_1                                        */
+  const void* w2;                /* [n2][n1]     fc_2                                        */
+  const float* w3;               /* [n2]         fc_out (always fp32)                        */
+  const float* b0;               /* [n0] */
+  const float* b1;               /* [n1] */
+  const float* b2;               /* [n2] */
+  const float* b3;               /* [1]  */
+} ListWeights;
+
+/* Gradient buffers for list_sdf_bwd; all fp32, all ACCUMULATED INTO (caller zeroes). */
+typedef struct ListGrads {
+  float* d_maps;                 /* [B][S][S][Cm]        or NULL */
+  float* d_vols[LIST_MAX_LEVELS];/* [B][R][R][R][C]      or NULL */
+  float* d_trans_mat;            /* [B][4][3]            or NULL */
+  float* d_w0;                   /* [n0][k_pad] (permuted columns) */
+  float* d_w1;                   /* [n1][n0] */
+  float* d_w2;                   /* [n2][n1] */
+  float* d_w3;                   /* [n2] */
+  float* d_b0; float* d_b1; float* d_b2; float* d_b3;
+} ListGrads;
+
+LIST_API int list_b200_abi_version(void);
+LIST_API const char* list_b200_last_error(void);
+
+/* Device check: 0 if the current device is sm_100 (B200), LIST_ENOSYS otherwise. */
+LIST_API int list_b200_device_ok(void);
+
+/* Column layout + permutation for a given channel configuration (host only, no CUDA).
+ * perm may be NULL; otherwise it receives k_out entries, perm[new_col] = reference col. */
+LIST_API int list_feature_layout(int32_t map_channels, int32_t n_levels, const int32_t* vol_ch,
+                        ListLayout* layout, int32_t* perm);
+
+/* a-1 hoisted (reference modules.py:25-35 + the per-chunk recomputation it implies):
+ * n_maps NCHW fp32 maps -> one channels-last [B][S][S][sum C] tensor of `dtype`,
+ * bilinear, align_corners=True.  Run once per image instead of once per chunk. */
+LIST_API int list_prep_maps(const float* const* maps_nchw, const int32_t* ch, const int32_t* size,
+                   int32_t n_maps, int32_t B, int32_t map_size, void* out, int32_t dtype,
+                   void* stream);
+
+/* NCDHW fp32 volume (reference modules.py:425-442 outputs) -> [B][R][R][R][C] of `dtype`. */
+LIST_API int list_prep_volume(const float* vol_ncdhw, int32_t B, int32_t C, int32_t R, void* out,
+                     int32_t dtype, void* stream);
+
+/* a-8 grid (reference utils.py:84-95): points [begin, begin+count) of the res^3 grid,
+ * x slowest / z fastest, float64 linspace rounded to fp32, written as (x,y,z) rows. */
+LIST_API int list_grid_points(float* q, int32_t res, double bb_min, double bb_max, int64_t begin,
+                     int64_t count, void* stream);
+
+/* a-2..a-5 (reference modules.py:37-53, 256-275; models.py:91-92): one fused
+ * transform-and-gather pass writing feature rows X[B*N][ldx] of ctx->dtype.
+ * q: [B][N][3] fp32.  q_is_raw != 0: q holds raw (x,y,z) in [-0.5,0.5] and the kernel
+ * applies the reference's [2,1,0] swap and *2; otherwise q is already swapped+scaled. */
+LIST_API int list_gather_fwd(const ListCtx* ctx, const float* q, int32_t q_is_raw, void* X, int64_t ldx,
+                    int32_t B, int64_t N, void* stream);
+
+/* Same rows for grid points [begin, begin+count) of image `image` without reading q:
+ * dense-grid specialisation of a-8 + a-2..a-5 (reference executors.py:215-220). */
+LIST_API int list_gather_grid_fwd(const ListCtx* ctx, int32_t image, int32_t res, double bb_min,
+                         double bb_max, int64_t begin, int64_t count, void* X, int64_t ldx,
+                         void* stream);
+
+/* a-6 (reference modules.py:276-282): sdf[r] = fc_out(relu(fc_2(relu(fc_1(relu(fc_0 X[r]))))))
+ * for `rows` feature rows; result divided by out_div (1 = the reference's scaled SDF,
+ * sdf_scale = executors.py:231).  LIST_BF16: tcgen05/TMEM kernel, needs no workspace.
+ * LIST_F32: FFMA kernels, workspace >= list_mlp_workspace_bytes(). */
+LIST_API size_t list_mlp_workspace_bytes(const ListWeights* w, int64_t rows);
+LIST_API int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf,
+                 float out_div, void* workspace, size_t workspace_bytes, void* stream);
+
+/* a-7: gather + MLP for explicit query points, chunked through `workspace`. */
+LIST_API size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_t chunk_rows);
+LIST_API int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw,
+                 int32_t B, int64_t N, float* sdf, float out_div, int64_t chunk_rows,
+                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
+ * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */
+LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min,
+                  double bb_max, int64_t begin, int64_t count, float* sdf, float sdf_scale,
+                  int64_t chunk_rows, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers end to end (the e2e path of bench.py): reference-layout fp32
+ * per-image tensors in (pinned) host memory -> H2D -> prep -> grid evaluation -> D2H of the
+ * SDF grid.  dev_scratch is a caller-owned DEVICE arena of >= list_sdf_grid_host_bytes(). */
+LIST_API size_t list_sdf_grid_host_bytes(const int32_t* map_ch, const int32_t* map_size_in, int32_t n_maps,
+                                int32_t map_size, int32_t n_levels, const int32_t* vol_ch,
+                                const int32_t* vol_res, int32_t B, int32_t dtype, int64_t count,
+                                int64_t chunk_rows);
+LIST_API int list_sdf_grid_host(const float* const* maps_nchw_host, const int32_t* map_ch,
+                       const int32_t* map_size_in, int32_t n_maps, int32_t map_size,
+                       const float* const* vols_ncdhw_host, int32_t n_levels, const int32_t* vol_ch,
+                       const int32_t* vol_res, const float* trans_mat_host, int32_t B, int32_t dtype,
+                       const ListWeights* w_dev, int32_t res, double bb_min, double bb_max,
+                       int64_t begin, int64_t count, float sdf_scale, int64_t chunk_rows,
+                       float* sdf_host, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* a-9 backward of a-2..a-6 for training (reference train.py:72-85 via autograd):
+ * given d_sdf[B*N] computes all gradients in ListGrads (fp32 path only).
+ * Needs the fp32 feature rows X and the saved activations in `workspace` from
+ * list_mlp_fwd on the same rows (same workspace pointer, untouched in between). */
+LIST_API size_t list_bwd_workspace_bytes(const ListWeights* w, int64_t rows);
+LIST_API int list_sdf_bwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw,
+                 int32_t B, int64_t N, const void* X, int64_t ldx, const void* fwd_workspace,
+                 const float* d_sdf, const ListGrads* grads, void* workspace,
+                 size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIST_B200_H */

@@ -1,0 +1,443 @@
+// extern "C" entry points of liblist_b200.so (declared in include/list_b200.h).
+// Argument validation, the row layout, chunk loops; the kernels live in the other .cu files.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace list {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return LIST_ECUDA;
+}
+
+// kernels / launchers defined in the other translation units
+int prep_maps(const float* const* maps, const int32_t* ch, const int32_t* size, int n_maps, int B, int S, void* out,
+              int dtype, cudaStream_t st);
+int prep_volume(const float* in, int B, int C, int R, void* out, int dtype, cudaStream_t st);
+int gather_fwd(const ListCtx* ctx, const float* q, int q_is_raw, void* X, int64_t ldx, int B, int64_t N, cudaStream_t st);
+int gather_grid_fwd(const ListCtx* ctx, int image, int res, double bb_min, double bb_max, int64_t begin, int64_t count,
+                    void* X, int64_t ldx, cudaStream_t st);
+int grid_points(float* q, int res, double lo, double hi, int64_t begin, int64_t count, cudaStream_t st);
+size_t mlp_f32_workspace_bytes(const ListWeights* w, int64_t rows);
+int mlp_f32_fwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows, float* sdf, float out_div, float* ws,
+                cudaStream_t st);
+size_t mlp_f32_bwd_workspace_bytes(const ListWeights* w, int64_t rows);
+int mlp_f32_bwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows, const float* fwd_ws, const float* d_sdf,
+                const ListGrads* g, float* ws, cudaStream_t st);
+int gather_bwd(const ListCtx* ctx, const float* q, int q_is_raw, int B, int64_t N, const float* dX, int64_t ldd,
+               const ListGrads* g, cudaStream_t st);
+int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
+               cudaStream_t st);
+
+static size_t elem_size(int dtype) { return dtype == LIST_BF16 ? 2 : 4; }
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int check_ctx(const ListCtx* c) {
+  LIST_CHECK_ARG(c != nullptr, "ctx is NULL");
+  LIST_CHECK_ARG(c->dtype == LIST_F32 || c->dtype == LIST_BF16, "ctx.dtype %d is not LIST_F32/LIST_BF16", c->dtype);
+  LIST_CHECK_ARG(c->B >= 1, "ctx.B %d < 1", c->B);
+  LIST_CHECK_ARG(c->map_size >= 2, "ctx.map_size %d < 2", c->map_size);
+  LIST_CHECK_ARG(c->map_channels > 0 && c->map_channels % 8 == 0, "ctx.map_channels %d must be a positive multiple of 8",
+                 c->map_channels);
+  LIST_CHECK_ARG(c->maps != nullptr && (reinterpret_cast<uintptr_t>(c->maps) & 15) == 0, "ctx.maps NULL or not 16B aligned");
+  LIST_CHECK_ARG(c->n_levels >= 1 && c->n_levels <= LIST_MAX_LEVELS, "ctx.n_levels %d out of range", c->n_levels);
+  for (int l = 0; l < c->n_levels; ++l) {
+    LIST_CHECK_ARG(c->vol_res[l] >= 1, "ctx.vol_res[%d]=%d < 1", l, c->vol_res[l]);
+    LIST_CHECK_ARG(c->vol_ch[l] >= 1 && c->vol_ch[l] <= 128, "ctx.vol_ch[%d]=%d not in [1,128]", l, c->vol_ch[l]);
+    LIST_CHECK_ARG(c->vols[l] != nullptr && (reinterpret_cast<uintptr_t>(c->vols[l]) & 15) == 0,
+                   "ctx.vols[%d] NULL or not 16B aligned", l);
+  }
+  LIST_CHECK_ARG(c->trans_mat != nullptr, "ctx.trans_mat is NULL");
+  return LIST_OK;
+}
+
+static int check_weights(const ListWeights* w, int k_pad) {
+  LIST_CHECK_ARG(w != nullptr, "weights is NULL");
+  LIST_CHECK_ARG(w->dtype == LIST_F32 || w->dtype == LIST_BF16, "weights.dtype %d invalid", w->dtype);
+  LIST_CHECK_ARG(k_pad < 0 || w->k_pad == k_pad, "weights.k_pad %d does not match the feature layout (%d)", w->k_pad, k_pad);
+  LIST_CHECK_ARG(w->n0 > 0 && w->n1 > 0 && w->n2 > 0 && w->n0 % 4 == 0 && w->n1 % 4 == 0 && w->n2 % 4 == 0,
+                 "weights layer widths %d/%d/%d must be positive multiples of 4", w->n0, w->n1, w->n2);
+  LIST_CHECK_ARG(w->w0 && w->w1 && w->w2 && w->w3 && w->b0 && w->b1 && w->b2 && w->b3, "a weights pointer is NULL");
+  LIST_CHECK_ARG(((reinterpret_cast<uintptr_t>(w->w0) | reinterpret_cast<uintptr_t>(w->w1) |
+                   reinterpret_cast<uintptr_t>(w->w2)) & 15) == 0, "weight matrices must be 16B aligned");
+  return LIST_OK;
+}
+
+static int mlp_variant() {
+  // LIST_B200_MLP_VARIANT=1 selects the single-CTA tcgen05 kernel (bring-up aid); default CTA pair.
+  const char* e = getenv("LIST_B200_MLP_VARIANT");
+  return (e && e[0] == '1') ? 1 : 2;
+}
+
+}  // namespace list
+
+using namespace list;
+
+extern "C" {
+
+int list_b200_abi_version(void) { return LIST_B200_ABI_VERSION; }
+const char* list_b200_last_error(void) { return g_err; }
+
+int list_b200_device_ok(void) {
+  int dev = 0;
+  LIST_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  LIST_CUDA(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; list_b200 is built for sm_100a (B200) only", dev, prop.major, prop.minor);
+    return LIST_ENOSYS;
+  }
+  return LIST_OK;
+}
+
+int list_feature_layout(int32_t map_channels, int32_t n_levels, const int32_t* vol_ch, ListLayout* layout, int32_t* perm) {
+  LIST_CHECK_ARG(layout != nullptr && vol_ch != nullptr, "layout/vol_ch is NULL");
+  LIST_CHECK_ARG(n_levels >= 1 && n_levels <= LIST_MAX_LEVELS, "n_levels %d out of range", n_levels);
+  LIST_CHECK_ARG(map_channels > 0 && map_channels % 8 == 0, "map_channels %d must be a positive multiple of 8", map_channels);
+  int sum_c = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    LIST_CHECK_ARG(vol_ch[l] >= 1, "vol_ch[%d]=%d < 1", l, vol_ch[l]);
+    sum_c += vol_ch[l];
+  }
+  memset(layout, 0, sizeof(*layout));
+  int col = 0;
+  layout->map_off = col;
+  col += map_channels;
+  // vector levels (C % 8 == 0) first, widest-index first, then the scalar levels, then q
+  for (int l = n_levels - 1; l >= 0; --l)
+    if (vol_ch[l] % 8 == 0) { layout->vol_off[l] = col; col += LIST_NUM_DISP * vol_ch[l]; }
+  for (int l = n_levels - 1; l >= 0; --l)
+    if (vol_ch[l] % 8 != 0) { layout->vol_off[l] = col; col += LIST_NUM_DISP * vol_ch[l]; }
+  layout->xyz_off = col;
+  col += 3;
+  layout->k_out = col;
+  layout->k_pad = (col + 63) / 64 * 64;
+  if (perm) {
+    // reference column of (level l, channel c, displacement d) = (cum_c[l] + c)*7 + d  (modules.py:270-273);
+    // percep follows at 7*sum_c, q at 7*sum_c + map_channels (modules.py:275).
+    int cum = 0;
+    for (int l = 0; l < n_levels; ++l) {
+      for (int d = 0; d < LIST_NUM_DISP; ++d)
+        for (int c = 0; c < vol_ch[l]; ++c) perm[layout->vol_off[l] + d * vol_ch[l] + c] = (cum + c) * LIST_NUM_DISP + d;
+      cum += vol_ch[l];
+    }
+    for (int c = 0; c < map_channels; ++c) perm[layout->map_off + c] = LIST_NUM_DISP * sum_c + c;
+    for (int j = 0; j < 3; ++j) perm[layout->xyz_off + j] = LIST_NUM_DISP * sum_c + map_channels + j;
+  }
+  return LIST_OK;
+}
+
+int list_prep_maps(const float* const* maps_nchw, const int32_t* ch, const int32_t* size, int32_t n_maps, int32_t B,
+                   int32_t map_size, void* out, int32_t dtype, void* stream) {
+  LIST_CHECK_ARG(maps_nchw && ch && size && out, "list_prep_maps: NULL argument");
+  LIST_CHECK_ARG(n_maps >= 1 && n_maps <= LIST_MAX_MAPS, "list_prep_maps: n_maps %d out of range", n_maps);
+  LIST_CHECK_ARG(dtype == LIST_F32 || dtype == LIST_BF16, "list_prep_maps: bad dtype %d", dtype);
+  LIST_CHECK_ARG(B >= 1 && map_size >= 2, "list_prep_maps: B=%d map_size=%d", B, map_size);
+  for (int i = 0; i < n_maps; ++i) {
+    LIST_CHECK_ARG(maps_nchw[i] != nullptr && ch[i] >= 1 && size[i] >= 1 && size[i] <= 1024,
+                   "list_prep_maps: map %d invalid (C=%d, size=%d)", i, ch[i], size[i]);
+  }
+  return prep_maps(maps_nchw, ch, size, n_maps, B, map_size, out, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int list_prep_volume(const float* vol, int32_t B, int32_t C, int32_t R, void* out, int32_t dtype, void* stream) {
+  LIST_CHECK_ARG(vol && out, "list_prep_volume: NULL argument");
+  LIST_CHECK_ARG(dtype == LIST_F32 || dtype == LIST_BF16, "list_prep_volume: bad dtype %d", dtype);
+  LIST_CHECK_ARG(B >= 1 && C >= 1 && C <= 128 && R >= 1, "list_prep_volume: B=%d C=%d R=%d", B, C, R);
+  return prep_volume(vol, B, C, R, out, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int list_grid_points(float* q, int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count, void* stream) {
+  LIST_CHECK_ARG(q != nullptr || count == 0, "list_grid_points: q is NULL");
+  LIST_CHECK_ARG(res >= 1 && res <= 2048, "list_grid_points: res %d out of range", res);
+  const int64_t total = static_cast<int64_t>(res) * res * res;
+  LIST_CHECK_ARG(begin >= 0 && count >= 0 && begin + count <= total, "list_grid_points: [%lld,+%lld) outside res^3",
+                 (long long)begin, (long long)count);
+  return grid_points(q, res, bb_min, bb_max, begin, count, static_cast<cudaStream_t>(stream));
+}
+
+int list_gather_fwd(const ListCtx* ctx, const float* q, int32_t q_is_raw, void* X, int64_t ldx, int32_t B, int64_t N,
+                    void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  LIST_CHECK_ARG(B == ctx->B, "list_gather_fwd: B %d != ctx.B %d", B, ctx->B);
+  LIST_CHECK_ARG(N >= 0, "list_gather_fwd: N < 0");
+  if (N == 0) return LIST_OK;
+  ListLayout lay;
+  if ((rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr))) return rc;
+  LIST_CHECK_ARG(q != nullptr && X != nullptr, "list_gather_fwd: q/X is NULL");
+  LIST_CHECK_ARG(ldx >= lay.k_pad && ldx % 8 == 0, "list_gather_fwd: ldx %lld must be >= %d and a multiple of 8", (long long)ldx, lay.k_pad);
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "list_gather_fwd: X not 16B aligned");
+  return gather_fwd(ctx, q, q_is_raw, X, ldx, B, N, static_cast<cudaStream_t>(stream));
+}
+
+int list_gather_grid_fwd(const ListCtx* ctx, int32_t image, int32_t res, double bb_min, double bb_max, int64_t begin,
+                         int64_t count, void* X, int64_t ldx, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_gather_grid_fwd: image %d outside [0,%d)", image, ctx->B);
+  LIST_CHECK_ARG(res >= 1 && res <= 2048, "list_gather_grid_fwd: res %d out of range", res);
+  const int64_t total = static_cast<int64_t>(res) * res * res;
+  LIST_CHECK_ARG(begin >= 0 && count >= 0 && begin + count <= total, "list_gather_grid_fwd: [%lld,+%lld) outside res^3",
+                 (long long)begin, (long long)count);
+  if (count == 0) return LIST_OK;
+  ListLayout lay;
+  if ((rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr))) return rc;
+  LIST_CHECK_ARG(X != nullptr && ldx >= lay.k_pad && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+                 "list_gather_grid_fwd: X NULL/unaligned or ldx %lld < %d", (long long)ldx, lay.k_pad);
+  return gather_grid_fwd(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, static_cast<cudaStream_t>(stream));
+}
+
+size_t list_mlp_workspace_bytes(const ListWeights* w, int64_t rows) {
+  if (!w || rows <= 0) return 0;
+  return w->dtype == LIST_F32 ? mlp_f32_workspace_bytes(w, rows) : 0;
+}
+
+int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  int rc = check_weights(w, -1);
+  if (rc) return rc;
+  LIST_CHECK_ARG(rows >= 0, "list_mlp_fwd: rows < 0");
+  if (rows == 0) return LIST_OK;
+  LIST_CHECK_ARG(X != nullptr && sdf != nullptr, "list_mlp_fwd: X/sdf is NULL");
+  LIST_CHECK_ARG(out_div != 0.f, "list_mlp_fwd: out_div must be non-zero");
+  LIST_CHECK_ARG(ldx >= w->k_pad && ldx % 8 == 0, "list_mlp_fwd: ldx %lld must be >= k_pad %d and a multiple of 8", (long long)ldx, w->k_pad);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (w->dtype == LIST_F32) {
+    LIST_CHECK_ARG(rows < (1LL << 31), "list_mlp_fwd: rows too large for one call");
+    const size_t need = mlp_f32_workspace_bytes(w, rows);
+    if (workspace == nullptr || workspace_bytes < need) {
+      set_error("list_mlp_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+      return LIST_ENOMEM;
+    }
+    return mlp_f32_fwd(w, static_cast<const float*>(X), ldx, rows, sdf, out_div, static_cast<float*>(workspace), st);
+  }
+  return mlp_tc_fwd(w, X, ldx, rows, sdf, out_div, mlp_variant(), st);
+}
+
+size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_t chunk_rows) {
+  if (!ctx || !w || chunk_rows <= 0) return 0;
+  ListLayout lay;
+  if (list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr)) return 0;
+  const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
+  return xb + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+}
+
+int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw, int32_t B, int64_t N, float* sdf,
+                 float out_div, int64_t chunk_rows, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  ListLayout lay;
+  if ((rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr))) return rc;
+  if ((rc = check_weights(w, lay.k_pad))) return rc;
+  LIST_CHECK_ARG(w->dtype == ctx->dtype, "list_sdf_fwd: weights.dtype %d != ctx.dtype %d", w->dtype, ctx->dtype);
+  LIST_CHECK_ARG(B == ctx->B && N >= 0, "list_sdf_fwd: B %d != ctx.B %d or N < 0", B, ctx->B);
+  if (N == 0) return LIST_OK;
+  LIST_CHECK_ARG(q && sdf && out_div != 0.f, "list_sdf_fwd: q/sdf NULL or out_div == 0");
+  LIST_CHECK_ARG(chunk_rows >= 1, "list_sdf_fwd: chunk_rows < 1");
+  const size_t need = list_sdf_workspace_bytes(ctx, w, chunk_rows);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("list_sdf_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
+    return LIST_ENOMEM;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
+  void* X = workspace;
+  void* mlp_ws = static_cast<char*>(workspace) + xb;
+  // per image, chunks of the point range; one image at a time keeps the ctx indexing trivial
+  ListCtx one = *ctx;
+  for (int b = 0; b < B; ++b) {
+    one.B = 1;
+    one.maps = static_cast<const char*>(ctx->maps) + static_cast<size_t>(b) * ctx->map_size * ctx->map_size * ctx->map_channels * elem_size(ctx->dtype);
+    for (int l = 0; l < ctx->n_levels; ++l) {
+      const size_t vox = static_cast<size_t>(ctx->vol_res[l]) * ctx->vol_res[l] * ctx->vol_res[l] * ctx->vol_ch[l];
+      one.vols[l] = static_cast<const char*>(ctx->vols[l]) + static_cast<size_t>(b) * vox * elem_size(ctx->dtype);
+    }
+    one.trans_mat = ctx->trans_mat + b * 12;
+    for (int64_t n0 = 0; n0 < N; n0 += chunk_rows) {
+      const int64_t n = (N - n0 < chunk_rows) ? (N - n0) : chunk_rows;
+      if ((rc = gather_fwd(&one, q + (static_cast<int64_t>(b) * N + n0) * 3, q_is_raw, X, lay.k_pad, 1, n, st))) return rc;
+      if ((rc = list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * N + n0, out_div, mlp_ws,
+                             workspace_bytes - xb, stream)))
+        return rc;
+    }
+  }
+  return LIST_OK;
+}
+
+int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
+                  int64_t count, float* sdf, float sdf_scale, int64_t chunk_rows, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  ListLayout lay;
+  if ((rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr))) return rc;
+  if ((rc = check_weights(w, lay.k_pad))) return rc;
+  LIST_CHECK_ARG(w->dtype == ctx->dtype, "list_sdf_grid: weights.dtype %d != ctx.dtype %d", w->dtype, ctx->dtype);
+  LIST_CHECK_ARG(res >= 1 && res <= 2048, "list_sdf_grid: res %d out of range", res);
+  const int64_t total = static_cast<int64_t>(res) * res * res;
+  LIST_CHECK_ARG(begin >= 0 && count >= 0 && begin + count <= total, "list_sdf_grid: [%lld,+%lld) outside res^3",
+                 (long long)begin, (long long)count);
+  if (count == 0) return LIST_OK;
+  LIST_CHECK_ARG(sdf != nullptr && sdf_scale != 0.f && chunk_rows >= 1, "list_sdf_grid: sdf NULL, sdf_scale 0 or chunk_rows < 1");
+  const size_t need = list_sdf_workspace_bytes(ctx, w, chunk_rows);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("list_sdf_grid: workspace %zu B < required %zu B", workspace_bytes, need);
+    return LIST_ENOMEM;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
+  void* X = workspace;
+  void* mlp_ws = static_cast<char*>(workspace) + xb;
+  for (int b = 0; b < ctx->B; ++b) {
+    for (int64_t n0 = 0; n0 < count; n0 += chunk_rows) {
+      const int64_t n = (count - n0 < chunk_rows) ? (count - n0) : chunk_rows;
+      if ((rc = gather_grid_fwd(ctx, b, res, bb_min, bb_max, begin + n0, n, X, lay.k_pad, st))) return rc;
+      if ((rc = list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, mlp_ws,
+                             workspace_bytes - xb, stream)))
+        return rc;
+    }
+  }
+  return LIST_OK;
+}
+
+// ---- host-buffer variant -----------------------------------------------------------------
+struct HostPlan {
+  size_t raw_maps[LIST_MAX_MAPS], raw_vols[LIST_MAX_LEVELS], raw_T, maps_cl, vols_cl[LIST_MAX_LEVELS], sdf, ws, total;
+};
+static void plan_host(const int32_t* map_ch, const int32_t* map_in, int n_maps, int S, int n_levels, const int32_t* vol_ch,
+                      const int32_t* vol_res, int B, int dtype, int64_t count, int64_t chunk_rows, HostPlan* p) {
+  size_t off = 0;
+  int cm = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += align_up(bytes, 256); return o; };
+  for (int i = 0; i < n_maps; ++i) { p->raw_maps[i] = take(static_cast<size_t>(B) * map_ch[i] * map_in[i] * map_in[i] * 4); cm += map_ch[i]; }
+  for (int l = 0; l < n_levels; ++l)
+    p->raw_vols[l] = take(static_cast<size_t>(B) * vol_ch[l] * vol_res[l] * vol_res[l] * vol_res[l] * 4);
+  p->raw_T = take(static_cast<size_t>(B) * 12 * 4);
+  p->maps_cl = take(static_cast<size_t>(B) * S * S * cm * elem_size(dtype));
+  for (int l = 0; l < n_levels; ++l)
+    p->vols_cl[l] = take(static_cast<size_t>(B) * vol_ch[l] * vol_res[l] * vol_res[l] * vol_res[l] * elem_size(dtype));
+  p->sdf = take(static_cast<size_t>(B) * count * 4);
+  ListLayout lay;
+  list_feature_layout(cm, n_levels, vol_ch, &lay, nullptr);
+  size_t ws = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(dtype), 256);
+  if (dtype == LIST_F32) ws += align_up(static_cast<size_t>(chunk_rows) * (512 + 256 + 256) * 4, 256);
+  p->ws = take(ws);
+  p->total = off;
+}
+
+size_t list_sdf_grid_host_bytes(const int32_t* map_ch, const int32_t* map_size_in, int32_t n_maps, int32_t map_size,
+                                int32_t n_levels, const int32_t* vol_ch, const int32_t* vol_res, int32_t B, int32_t dtype,
+                                int64_t count, int64_t chunk_rows) {
+  if (!map_ch || !map_size_in || !vol_ch || !vol_res || n_maps < 1 || n_maps > LIST_MAX_MAPS || n_levels < 1 ||
+      n_levels > LIST_MAX_LEVELS || B < 1 || count < 0 || chunk_rows < 1)
+    return 0;
+  HostPlan p;
+  plan_host(map_ch, map_size_in, n_maps, map_size, n_levels, vol_ch, vol_res, B, dtype, count, chunk_rows, &p);
+  return p.total;
+}
+
+int list_sdf_grid_host(const float* const* maps_host, const int32_t* map_ch, const int32_t* map_size_in, int32_t n_maps,
+                       int32_t map_size, const float* const* vols_host, int32_t n_levels, const int32_t* vol_ch,
+                       const int32_t* vol_res, const float* trans_mat_host, int32_t B, int32_t dtype, const ListWeights* w_dev,
+                       int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count, float sdf_scale,
+                       int64_t chunk_rows, float* sdf_host, void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+  LIST_CHECK_ARG(maps_host && map_ch && map_size_in && vols_host && vol_ch && vol_res && trans_mat_host && w_dev && sdf_host,
+                 "list_sdf_grid_host: NULL argument");
+  LIST_CHECK_ARG(n_maps >= 1 && n_maps <= LIST_MAX_MAPS && n_levels >= 1 && n_levels <= LIST_MAX_LEVELS && B >= 1 &&
+                 count >= 0 && chunk_rows >= 1, "list_sdf_grid_host: bad sizes");
+  LIST_CHECK_ARG(dtype == LIST_F32 || dtype == LIST_BF16, "list_sdf_grid_host: bad dtype %d", dtype);
+  LIST_CHECK_ARG(w_dev->n0 == 512 && w_dev->n1 == 256 && w_dev->n2 == 256, "list_sdf_grid_host: layer widths must be 512/256/256");
+  HostPlan p;
+  plan_host(map_ch, map_size_in, n_maps, map_size, n_levels, vol_ch, vol_res, B, dtype, count, chunk_rows, &p);
+  if (!dev_scratch || dev_scratch_bytes < p.total) {
+    set_error("list_sdf_grid_host: dev_scratch %zu B < required %zu B", dev_scratch_bytes, p.total);
+    return LIST_ENOMEM;
+  }
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(dev_scratch) & 255) == 0, "list_sdf_grid_host: dev_scratch must be 256B aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(dev_scratch);
+  const float* dmaps[LIST_MAX_MAPS];
+  int cm = 0;
+  for (int i = 0; i < n_maps; ++i) {
+    const size_t bytes = static_cast<size_t>(B) * map_ch[i] * map_size_in[i] * map_size_in[i] * 4;
+    LIST_CUDA(cudaMemcpyAsync(base + p.raw_maps[i], maps_host[i], bytes, cudaMemcpyHostToDevice, st));
+    dmaps[i] = reinterpret_cast<const float*>(base + p.raw_maps[i]);
+    cm += map_ch[i];
+  }
+  for (int l = 0; l < n_levels; ++l) {
+    const size_t bytes = static_cast<size_t>(B) * vol_ch[l] * vol_res[l] * vol_res[l] * vol_res[l] * 4;
+    LIST_CUDA(cudaMemcpyAsync(base + p.raw_vols[l], vols_host[l], bytes, cudaMemcpyHostToDevice, st));
+  }
+  LIST_CUDA(cudaMemcpyAsync(base + p.raw_T, trans_mat_host, static_cast<size_t>(B) * 48, cudaMemcpyHostToDevice, st));
+  int rc;
+  if ((rc = list_prep_maps(dmaps, map_ch, map_size_in, n_maps, B, map_size, base + p.maps_cl, dtype, stream))) return rc;
+  ListCtx ctx{};
+  ctx.B = B;
+  ctx.dtype = dtype;
+  ctx.map_size = map_size;
+  ctx.map_channels = cm;
+  ctx.maps = base + p.maps_cl;
+  ctx.n_levels = n_levels;
+  for (int l = 0; l < n_levels; ++l) {
+    if ((rc = list_prep_volume(reinterpret_cast<const float*>(base + p.raw_vols[l]), B, vol_ch[l], vol_res[l],
+                               base + p.vols_cl[l], dtype, stream)))
+      return rc;
+    ctx.vol_res[l] = vol_res[l];
+    ctx.vol_ch[l] = vol_ch[l];
+    ctx.vols[l] = base + p.vols_cl[l];
+  }
+  ctx.trans_mat = reinterpret_cast<const float*>(base + p.raw_T);
+  float* dsdf = reinterpret_cast<float*>(base + p.sdf);
+  if ((rc = list_sdf_grid(&ctx, w_dev, res, bb_min, bb_max, begin, count, dsdf, sdf_scale, chunk_rows, base + p.ws, p.total - p.ws, stream)))
+    return rc;
+  LIST_CUDA(cudaMemcpyAsync(sdf_host, dsdf, static_cast<size_t>(B) * count * 4, cudaMemcpyDeviceToHost, st));
+  return LIST_OK;
+}
+
+// ---- backward ------------------------------------------------------------------------------
+size_t list_bwd_workspace_bytes(const ListWeights* w, int64_t rows) {
+  if (!w || rows <= 0) return 0;
+  return mlp_f32_bwd_workspace_bytes(w, rows);
+}
+
+int list_sdf_bwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw, int32_t B, int64_t N, const void* X,
+                 int64_t ldx, const void* fwd_workspace, const float* d_sdf, const ListGrads* grads, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  ListLayout lay;
+  if ((rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr))) return rc;
+  if ((rc = check_weights(w, lay.k_pad))) return rc;
+  LIST_CHECK_ARG(ctx->dtype == LIST_F32 && w->dtype == LIST_F32, "list_sdf_bwd: the backward path is fp32 only");
+  LIST_CHECK_ARG(B == ctx->B && N >= 0, "list_sdf_bwd: B %d != ctx.B %d or N < 0", B, ctx->B);
+  const int64_t rows = static_cast<int64_t>(B) * N;
+  if (rows == 0) return LIST_OK;
+  LIST_CHECK_ARG(rows < (1LL << 31), "list_sdf_bwd: too many rows for one call");
+  LIST_CHECK_ARG(q && X && fwd_workspace && d_sdf && grads, "list_sdf_bwd: NULL argument");
+  LIST_CHECK_ARG(ldx >= lay.k_pad && ldx % 4 == 0, "list_sdf_bwd: bad ldx %lld", (long long)ldx);
+  const size_t need = mlp_f32_bwd_workspace_bytes(w, rows);
+  if (!workspace || workspace_bytes < need) {
+    set_error("list_sdf_bwd: workspace %zu B < required %zu B", workspace_bytes, need);
+    return LIST_ENOMEM;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = mlp_f32_bwd(w, static_cast<const float*>(X), ldx, rows, static_cast<const float*>(fwd_workspace), d_sdf, grads,
+                        static_cast<float*>(workspace), st)))
+    return rc;
+  return gather_bwd(ctx, q, q_is_raw, B, N, static_cast<const float*>(workspace), lay.k_pad, grads, st);
+}
+
+}  // extern "C"

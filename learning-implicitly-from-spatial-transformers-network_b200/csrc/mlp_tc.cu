@@ -1,0 +1,520 @@
+// bf16 tensor-core implicit MLP (row a-6, reference network/modules.py:196-201, 276-282):
+//   sdf = fc_out(relu(fc_2(relu(fc_1(relu(fc_0 x))))))      3610(->3648) -> 512 -> 256 -> 256 -> 1
+// as ONE persistent warp-specialised sm_100a kernel.  Per CTA a 128-row tile of X runs through
+// all four layers without leaving the SM:
+//
+//   TMA (cp.async.bulk.tensor, 128B swizzle) streams X[128 x 64] and weight[128 x 64] boxes into
+//   a shared-memory ring;  tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulates in TMEM;
+//   fc_0's 128x512 fp32 accumulator fills all 512 TMEM columns;  the epilogue warps read it with
+//   tcgen05.ld, add bias, ReLU, round to bf16 and write it BACK to TMEM (tcgen05.st) as the
+//   A operand of fc_1 (A-from-TMEM MMA), likewise for fc_2;  fc_out (256 -> 1) is a register dot
+//   product in the last epilogue.  The feature concat was already done by the gather kernel's
+//   row layout, biases / activations / the final /sdf_scale are fused here.
+//
+//   TMEM columns : fc_0 acc [0,512) -> H1 bf16 [0,256) -> fc_1 acc [256,512) -> H2 bf16 [0,128)
+//                  -> fc_2 acc [256,512).
+//   Warp roles   : warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one thread),
+//                  warps 2..5 = epilogue (one TMEM lane quarter each).
+//   CG = 2       : a CTA pair (cluster 2x1x1) runs tcgen05.mma.cta_group::2 (M = 256): each CTA
+//                  loads its own 128 rows of X and HALF of every weight tile, which halves the
+//                  L2 -> SM weight traffic per row -- the real bound of this kernel, since W0
+//                  (3.7 MB) is re-streamed for every row tile.
+#include <cuda.h>
+
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace list {
+namespace tc {
+
+constexpr int BM = 128;                 // rows per CTA
+constexpr int BK = 64;                  // bf16 elements per K chunk = 128 B = one swizzle atom row
+constexpr int N0 = 512, N1 = 256, N2 = 256;
+constexpr int A_BYTES = BM * BK * 2;    // 16 KB
+constexpr int SUB_BYTES = 128 * BK * 2; // one 128-row weight box, 16 KB
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+constexpr uint32_t kTmemCols = 512;
+
+template <int CG>
+struct Cfg {
+  static constexpr int SUBS_L0 = (N0 / 128) / CG;     // weight boxes per CTA per fc_0 chunk
+  static constexpr int SUBS_L12 = (N1 / 128) / CG;    // per fc_1 / fc_2 chunk
+  static constexpr int STAGE_BYTES = A_BYTES + SUBS_L0 * SUB_BYTES;
+  static constexpr int STAGES = CG == 1 ? 2 : 4;
+  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;   // b0 b1 b2 w3
+  static constexpr int BAR_OFF = RING_BYTES + PARAM_FLOATS * 4;
+  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 2) * 8 + 16 + 1024 /*align slack*/;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 4000000000LL) {
+      printf("list_b200 mlp_tc: mbarrier timeout (block %d thread %d bar %u parity %u)\n", blockIdx.x,
+             threadIdx.x, bar, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+// 2-D box load; `bar` is a shared::cluster mbarrier address (possibly the peer CTA's).
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint32_t bar, uint32_t dst, int c0, int c1) {
+  if (CG == 1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  } else {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+template <int CG>
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem) {
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kTmemCols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(kTmemCols) : "memory");
+}
+
+// UMMA shared-memory descriptor, K-major, 128B swizzle: rows are 128 B, 8-row groups 1024 B
+// apart (SBO), start address in 16 B units, descriptor version 1 (sm_100), layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);   // start address   [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                        // LBO (unused for swizzled K-major)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;                // SBO             [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                        // version = 1
+  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
+  return d;
+}
+// Instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+template <int CG>
+__device__ __forceinline__ void umma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if (CG == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+  }
+}
+template <int CG>
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  if (CG == 1) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+  } else {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+  }
+}
+// Arrive on `bar` (same offset in every CTA of the pair) when all MMAs issued so far retire.
+template <int CG>
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  if (CG == 1) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  } else {
+    const uint16_t mask = 3;
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t u[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]),
+        "r"(u[8]), "r"(u[9]), "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------ kernel
+template <int CG>
+__global__ void __launch_bounds__(kThreads, 1)
+mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
+              const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+              const float* __restrict__ b0, const float* __restrict__ b1, const float* __restrict__ b2,
+              const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ sdf,
+              long long rows, int nk0, float out_div) {
+  using C = Cfg<CG>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* const gbase = smem_raw + (base - raw);
+  float* const s_par = reinterpret_cast<float*>(gbase + C::RING_BYTES);
+  float* const s_b0 = s_par;
+  float* const s_b1 = s_b0 + N0;
+  float* const s_b2 = s_b1 + N1;
+  float* const s_w3 = s_b2 + N2;
+  const uint32_t bar0 = base + C::BAR_OFF;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
+  const uint32_t dfull_bar = bar0 + 8u * (2 * C::STAGES);
+  const uint32_t hready_bar = dfull_bar + 8u;
+  const uint32_t tmem_slot = hready_bar + 8u;
+  volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + C::BAR_OFF + (2 * C::STAGES + 2) * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+  const long long rows_per_tile = static_cast<long long>(BM) * CG;
+  const int num_tiles = static_cast<int>((rows + rows_per_tile - 1) / rows_per_tile);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW0);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(dfull_bar, 1);
+    mbar_init(hready_bar, 128 * CG);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_slot);
+  if (warp >= kEpiWarp0) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < C::PARAM_FLOATS; i += 128) {
+      float v;
+      if (i < N0) v = __ldg(b0 + i);
+      else if (i < N0 + N1) v = __ldg(b1 + i - N0);
+      else if (i < N0 + N1 + N2) v = __ldg(b2 + i - N0 - N1);
+      else v = __ldg(w3 + i - N0 - N1 - N2);
+      s_par[i] = v;
+    }
+  }
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const uint32_t stage0 = base;
+  auto stage_a = [&](int s) { return stage0 + static_cast<uint32_t>(s) * C::STAGE_BYTES; };
+  auto stage_b = [&](int s) { return stage0 + static_cast<uint32_t>(s) * C::STAGE_BYTES + A_BYTES; };
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      uint32_t slot = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int row0 = static_cast<int>(tile * rows_per_tile + rank * BM);
+        for (int kc = 0; kc < nk0; ++kc, ++slot) {                    // fc_0: X chunk + W0 chunk
+          const int s = slot % C::STAGES;
+          mbar_wait(empty_bar(s), ((slot / C::STAGES) & 1) ^ 1);
+          const uint32_t fb = (CG == 2) ? mapa(full_bar(s), 0) : full_bar(s);
+          if (rank == 0) mbar_expect_tx(full_bar(s), CG * C::STAGE_BYTES);
+          tma_load_2d<CG>(&tmX, fb, stage_a(s), kc * BK, row0);
+#pragma unroll
+          for (int j = 0; j < C::SUBS_L0; ++j) {
+            const int wrow = (CG == 1) ? j * 128 : j * 256 + static_cast<int>(rank) * 128;
+            tma_load_2d<CG>(&tmW0, fb, stage_b(s) + j * SUB_BYTES, kc * BK, wrow);
+          }
+        }
+#pragma unroll 1
+        for (int layer = 1; layer <= 2; ++layer) {                    // fc_1 / fc_2: weights only
+          const CUtensorMap* tm = (layer == 1) ? &tmW1 : &tmW2;
+          const int nk = (layer == 1 ? N0 : N1) / BK;
+          for (int kc = 0; kc < nk; ++kc, ++slot) {
+            const int s = slot % C::STAGES;
+            mbar_wait(empty_bar(s), ((slot / C::STAGES) & 1) ^ 1);
+            const uint32_t fb = (CG == 2) ? mapa(full_bar(s), 0) : full_bar(s);
+            if (rank == 0) mbar_expect_tx(full_bar(s), CG * C::SUBS_L12 * SUB_BYTES);
+#pragma unroll
+            for (int j = 0; j < C::SUBS_L12; ++j) {
+              const int wrow = (CG == 1) ? j * 128 : static_cast<int>(rank) * 128;
+              tma_load_2d<CG>(tm, fb, stage_b(s) + j * SUB_BYTES, kc * BK, wrow);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA, one thread) ===========================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128 * CG, 256);
+      constexpr uint32_t kInstrB = (256 / CG) * BK * 2;             // bytes of B one N=256 instruction reads per CTA
+      uint32_t slot = 0, hphase = 0;
+      bool first = true;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        if (!first) { mbar_wait(hready_bar, hphase); hphase ^= 1; }   // previous tile's accumulators drained
+        first = false;
+        tc_fence_after();
+        // ---- fc_0: D[0,512) = X · W0^T ----
+        for (int kc = 0; kc < nk0; ++kc, ++slot) {
+          const int s = slot % C::STAGES;
+          mbar_wait(full_bar(s), (slot / C::STAGES) & 1);
+          tc_fence_after();
+          const uint64_t ad = umma_desc_sw128(stage_a(s));
+          const uint64_t bd = umma_desc_sw128(stage_b(s));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              umma_ss<CG>(tmem_base + i * 256, ad + 2 * k, bd + ((i * kInstrB) >> 4) + 2 * k, idesc,
+                          (kc | k) != 0 ? 1u : 0u);
+            }
+          }
+          umma_commit<CG>(empty_bar(s));
+        }
+        umma_commit<CG>(dfull_bar);
+        // ---- fc_1: D[256,512) = H1(TMEM [0,256)) · W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) · W2^T ----
+#pragma unroll 1
+        for (int layer = 1; layer <= 2; ++layer) {
+          const int nk = (layer == 1 ? N0 : N1) / BK;
+          mbar_wait(hready_bar, hphase); hphase ^= 1;
+          tc_fence_after();
+          for (int kc = 0; kc < nk; ++kc, ++slot) {
+            const int s = slot % C::STAGES;
+            mbar_wait(full_bar(s), (slot / C::STAGES) & 1);
+            tc_fence_after();
+            const uint64_t bd = umma_desc_sw128(stage_b(s));
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k) {
+              // A operand: 16 bf16 of K = 8 TMEM columns
+              umma_ts<CG>(tmem_base + 256, tmem_base + kc * (BK / 2) + k * 8, bd + 2 * k, idesc,
+                          (kc | k) != 0 ? 1u : 0u);
+            }
+            umma_commit<CG>(empty_bar(s));
+          }
+          umma_commit<CG>(dfull_bar);
+        }
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int quarter = warp & 3;                                      // TMEM lane quarter this warp may touch
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t hready_remote = (CG == 2) ? mapa(hready_bar, 0) : hready_bar;
+    const float bias3 = __ldg(b3);
+    uint32_t dphase = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      const long long row = tile * rows_per_tile + rank * BM + quarter * 32 + lane;
+      // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
+      mbar_wait(dfull_bar, dphase); dphase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < N0 / 32; ++j) {
+        uint32_t v[32], u[16];
+        tmem_ld32(tq + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_b0 + j * 32 + 2 * i);
+          u[i] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f),
+                             fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
+        }
+        tmem_st16(tq + j * 16, u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      if (CG == 2) mbar_arrive_cluster(hready_remote);
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) ----
+      mbar_wait(dfull_bar, dphase); dphase ^= 1;
+      tc_fence_after();
+#pragma unroll 1
+      for (int j = 0; j < N1 / 32; ++j) {
+        uint32_t v[32], u[16];
+        tmem_ld32(tq + 256 + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_b1 + j * 32 + 2 * i);
+          u[i] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f),
+                             fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
+        }
+        tmem_st16(tq + j * 16, u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      if (CG == 2) mbar_arrive_cluster(hready_remote);
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      // ---- after fc_2: sdf = (relu(acc + b2) · w3 + b3) / out_div ----
+      mbar_wait(dfull_bar, dphase); dphase ^= 1;
+      tc_fence_after();
+      float acc = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < N2 / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tq + 256 + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          acc = fmaf(fmaxf(__uint_as_float(v[i]) + s_b2[j * 32 + i], 0.f), s_w3[j * 32 + i], acc);
+      }
+      tc_fence_before();
+      if (CG == 2) mbar_arrive_cluster(hready_remote);
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      if (row < rows) sdf[row] = __fdiv_rn(acc + bias3, out_div);
+    }
+  }
+
+  // =========================== teardown ===========================
+  tc_fence_before();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess) return nullptr;
+    if (qres != cudaDriverEntryPointSuccess) return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// bf16 row-major [outer][inner] with row pitch `pitch_elems`; box = 64 x 128, 128B swizzle.
+static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t pitch_elems) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return LIST_ENOSYS; }
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {pitch_elems * 2};
+  const cuuint32_t box[2] = {BK, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r)); return LIST_ECUDA; }
+  return LIST_OK;
+}
+
+template <int CG>
+static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div,
+                  cudaStream_t st) {
+  using C = Cfg<CG>;
+  CUtensorMap tmX, tmW0, tmW1, tmW2;
+  int rc;
+  if ((rc = make_map(&tmX, X, w->k_pad, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx)))) return rc;
+  if ((rc = make_map(&tmW0, w->w0, w->k_pad, N0, w->k_pad))) return rc;
+  if ((rc = make_map(&tmW1, w->w1, N0, N1, N0))) return rc;
+  if ((rc = make_map(&tmW2, w->w2, N1, N2, N1))) return rc;
+  int dev = 0, sms = 0;
+  LIST_CUDA(cudaGetDevice(&dev));
+  LIST_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  LIST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  const int64_t rows_per_tile = static_cast<int64_t>(BM) * CG;
+  const int64_t tiles = (rows + rows_per_tile - 1) / rows_per_tile;
+  const int clusters = static_cast<int>(tiles < (sms / CG) ? tiles : (sms / CG));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int nk0 = w->k_pad / BK;
+  LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
+                               sdf, static_cast<long long>(rows), nk0, out_div));
+  return LIST_OK;
+}
+
+}  // namespace tc
+
+// variant: 1 = single-CTA tcgen05 (cta_group::1), 2 = CTA pair (cta_group::2)
+int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
+               cudaStream_t st) {
+  if (rows == 0) return LIST_OK;
+  LIST_CHECK_ARG(w->n0 == tc::N0 && w->n1 == tc::N1 && w->n2 == tc::N2,
+                 "mlp_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
+  LIST_CHECK_ARG(w->k_pad % tc::BK == 0 && w->k_pad > 0, "mlp_tc: k_pad %d must be a positive multiple of 64", w->k_pad);
+  LIST_CHECK_ARG(ldx % 8 == 0 && ldx >= w->k_pad, "mlp_tc: ldx %lld must be >= k_pad and a multiple of 8", (long long)ldx);
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "mlp_tc: X must be 16-byte aligned");
+  LIST_CHECK_ARG(rows < (1LL << 31), "mlp_tc: rows %lld too large for one call", (long long)rows);
+  if (variant == 1) return tc::launch<1>(w, X, ldx, rows, sdf, out_div, st);
+  return tc::launch<2>(w, X, ldx, rows, sdf, out_div, st);
+}
+
+}  // namespace list

@@ -1,0 +1,261 @@
+"""GPU parity tests: the CUDA path through the C ABI against the oracle / the reference's golden
+vectors.  Tolerances are BASELINE.json's: max|dSDF| <= 1e-4 in fp32, <= 2e-2 in bf16."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from list_b200 import hotpath, synth
+from oracle import list_oracle as O
+from oracle import ref_port as P
+from tests.helpers import GOLDEN, load_case, singular_mask
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+DEV = "cuda:0"
+CASES = ["small_camera_b2", "small_random_b1", "full_camera_b1", "full_random_b1", "train_b2"]
+
+
+def ctx_and_weights(g, mode):
+    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, mode)
+    return ctx, hotpath.prepare_weights(g.weights, ctx.layout, mode)
+
+
+# ------------------------------------------------------------------ stage by stage (fp32)
+def test_prep_maps_matches_upsample_oracle():
+    inp = synth.make_inputs(seed=1, B=2, N=8, size="small")
+    g = inp.to(DEV)
+    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "fp32")
+    ref = O.prepare_maps(inp.maps)
+    assert ctx.maps_cl.shape == ref.shape
+    assert (ctx.maps_cl.cpu() - ref).abs().max().item() <= 2e-6
+    ctx16 = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "bf16")
+    assert (ctx16.maps_cl.float().cpu() - ref).abs().max().item() <= 2e-2
+    assert torch.equal(ctx16.maps_cl.cpu(), ctx.maps_cl.bfloat16().cpu())
+
+
+def test_prep_volume_is_an_exact_transpose():
+    inp = synth.make_inputs(seed=2, B=2, N=8, size="small")
+    g = inp.to(DEV)
+    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "fp32")
+    for v, cl in zip(inp.vols, ctx.vols_cl):
+        assert torch.equal(cl.cpu(), v.permute(0, 2, 3, 4, 1).contiguous())
+    ctx16 = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "bf16")
+    for v, cl in zip(inp.vols, ctx16.vols_cl):
+        assert torch.equal(cl.cpu(), v.permute(0, 2, 3, 4, 1).contiguous().bfloat16())
+
+
+@pytest.mark.parametrize("trans", ["camera", "random"])
+def test_gather_rows_match_oracle_feature_rows(trans):
+    inp = synth.make_inputs(seed=3, B=2, N=333, size="small", trans=trans)
+    g = inp.to(DEV)
+    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "fp32")
+    lay = ctx.layout
+    X = hotpath.gather_features(ctx, g.points, raw=True).cpu()
+    assert X.shape == (2 * 333, lay.k_pad)
+    assert torch.equal(X[:, lay.k_out:], torch.zeros(2 * 333, lay.k_pad - lay.k_out))      # zero padding
+    ref = O.feature_rows(inp.maps, inp.vols, inp.trans_mat, inp.points, fused_localise=True).reshape(-1, lay.k_out)
+    got = torch.empty_like(ref)
+    got[:, torch.from_numpy(lay.perm.astype(np.int64))] = X[:, :lay.k_out]                 # back to reference order
+    bad = singular_mask(inp).reshape(-1)
+    assert bad.float().mean() < 0.02
+    assert (got - ref)[~bad].abs().max().item() <= 2e-5
+    # swapped+scaled input convention gives the same rows
+    q = (g.points[:, :, [2, 1, 0]] * 2).contiguous()
+    assert torch.equal(hotpath.gather_features(ctx, q, raw=False).cpu(), X)
+
+
+def test_gather_nan_divide_and_out_of_range_points():
+    inp = synth.make_inputs(seed=4, B=1, N=64, size="small")
+    inp.points = (torch.rand(1, 64, 3, generator=torch.Generator().manual_seed(5)) - 0.5) * 3.0   # beyond the box
+    T = torch.zeros(1, 4, 3)
+    T[0, 3, 2] = -1e-8            # h2 + 1e-8 == 0 and numerators 0 -> 0/0 (NaN grid -> zero 2-D features)
+    inp.trans_mat = T
+    g = inp.to(DEV)
+    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "fp32")
+    lay = ctx.layout
+    X = hotpath.gather_features(ctx, g.points).cpu()
+    assert torch.isfinite(X).all()
+    assert torch.equal(X[:, lay.map_off:lay.map_off + 1024], torch.zeros(64, 1024))
+    ref = O.feature_rows(inp.maps, inp.vols, inp.trans_mat, inp.points).reshape(-1, lay.k_out)
+    got = torch.empty_like(ref)
+    got[:, torch.from_numpy(lay.perm.astype(np.int64))] = X[:, :lay.k_out]
+    assert (got - ref).abs().max().item() <= 2e-5
+
+
+def test_grid_points_bit_exact():
+    z = np.load(os.path.join(GOLDEN, "grid_points.npz"))
+    g5 = hotpath.grid_points(5).cpu().numpy()
+    assert np.array_equal(g5, z["g5"].astype(np.float32))
+    for res in (64, 256):
+        ax = z[f"ax{res}_f32"]
+        pts = hotpath.grid_points(res, begin=res * res * 3 + res * 5, count=res).cpu().numpy()   # x=3, y=5, z=0..res-1
+        assert np.array_equal(pts[:, 2], ax) and np.all(pts[:, 0] == ax[3]) and np.all(pts[:, 1] == ax[5])
+    full = hotpath.grid_points(64).cpu().numpy()
+    assert np.array_equal(full[:130], z["g64_f32_head"]) and np.array_equal(full[-130:], z["g64_f32_tail"])
+    assert np.array_equal(full, O.create_grid_points_from_bounds(-0.5, 0.5, 64).astype(np.float32))
+
+
+def test_mlp_fp32_matches_oracle():
+    gen = torch.Generator().manual_seed(6)
+    lay = hotpath.feature_layout(1024, [1, 16, 32, 64, 128, 128])
+    w = synth.mlp_weights(lay.k_out, gen)
+    Xr = torch.randn(777, lay.k_out, generator=gen)                  # reference column order
+    ref = O.implicit_mlp(Xr.unsqueeze(0), w)[0]
+    X = torch.zeros(777, lay.k_pad)
+    X[:, :lay.k_out] = Xr[:, torch.from_numpy(lay.perm.astype(np.int64))]
+    kw = hotpath.prepare_weights({k: v.to(DEV) for k, v in w.items()}, lay, "fp32")
+    out = hotpath.mlp(kw, X.to(DEV)).cpu()
+    assert (out - ref).abs().max().item() <= 1e-5
+
+
+# ------------------------------------------------------------------ end to end vs the reference's golden vectors
+@pytest.mark.parametrize("name", CASES)
+def test_fp32_path_vs_reference_golden(name):
+    inp, z, _ = load_case(name)
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "fp32")
+    sdf = hotpath.query_sdf(ctx, kw, g.points, chunk_rows=1000).cpu().numpy()
+    bad = singular_mask(inp).numpy()
+    err = np.abs(sdf - z["sdf"])
+    print(f"{name}: fp32 max|dSDF| = {err[~bad].max():.3e}, ill-conditioned points skipped: {int(bad.sum())}")
+    assert bad.mean() < 0.01
+    assert err[~bad].max() <= FP32_TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_bf16_path_vs_reference_golden(name):
+    inp, z, _ = load_case(name)
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "bf16")
+    sdf = hotpath.query_sdf(ctx, kw, g.points).cpu().numpy()
+    bad = singular_mask(inp, rel=1e-2).numpy()
+    err = np.abs(sdf - z["sdf"])
+    print(f"{name}: bf16 max|dSDF| = {err[~bad].max():.3e}")
+    assert np.isfinite(sdf).all()
+    assert err[~bad].max() <= BF16_TOL
+    assert np.median(err) <= 2e-3          # far inside the bound on typical points
+
+
+# ------------------------------------------------------------------ dense grid (a-8) and size-independent properties
+def test_dense_grid_32_vs_oracle_and_sign_pattern():
+    inp = synth.make_inputs(seed=8, B=1, N=8, size="small", trans="camera")
+    ref = P.dense_grid_sdf(inp.maps, inp.vols, inp.trans_mat, inp.weights, 32, sdf_scale=10.0, chunk=8192)
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "fp32")
+    got = hotpath.grid_sdf(ctx, kw, 32, sdf_scale=10.0, chunk_rows=5000)[0].view(32, 32, 32).cpu().numpy()
+    err = np.abs(got - ref)
+    assert err.max() <= FP32_TOL
+    # "identical marching-cubes topology": every vertex has the reference's sign, except vertices whose
+    # |SDF| is within the fp32 tolerance of 0 (listed, must be inside the tolerance)
+    flipped = np.sign(got) != np.sign(ref)
+    assert np.all(np.abs(ref[flipped]) <= FP32_TOL)
+    cells_changed = int((O.mc_case_index(got) != O.mc_case_index(ref)).sum())
+    print(f"grid 32^3: max|dSDF|={err.max():.2e}, flipped vertices={int(flipped.sum())}, MC cells changed={cells_changed}")
+
+
+@pytest.mark.parametrize("mode", ["fp32", "bf16"])
+def test_grid_kernel_equals_explicit_points_and_shards_compose(mode):
+    """gather_grid(begin,count) == gather(explicit grid points), and a grid evaluated in shards /
+    chunks of any size is bit-identical to one pass (what multi-GPU sharding relies on)."""
+    inp = synth.make_inputs(seed=9, B=2, N=8, size="small", trans="random")
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, mode)
+    res = 24
+    total = res ** 3
+    whole = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=total)
+    pts = hotpath.grid_points(res).unsqueeze(0).expand(2, -1, -1).contiguous()
+    explicit = hotpath.query_sdf(ctx, kw, pts, out_div=10.0, chunk_rows=4096)
+    assert torch.equal(whole, explicit)
+    parts = []
+    for begin, count in ((0, 1000), (1000, 5000), (6000, total - 6000)):
+        parts.append(hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=777))
+    assert torch.equal(torch.cat(parts, dim=1), whole)
+
+
+def test_point_permutation_and_batch_independence():
+    inp = synth.make_inputs(seed=10, B=2, N=500, size="small")
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "fp32")
+    a = hotpath.query_sdf(ctx, kw, g.points)
+    perm = torch.randperm(500, generator=torch.Generator().manual_seed(0)).to(DEV)
+    b = hotpath.query_sdf(ctx, kw, g.points[:, perm].contiguous())
+    assert torch.equal(a[:, perm], b)
+    # image 1 alone gives the rows of image 1 in the batch
+    one = synth.HotPathInputs([m[1:] for m in g.maps], [v[1:] for v in g.vols], g.trans_mat[1:], g.points[1:], g.weights)
+    ctx1, _ = ctx_and_weights(one, "fp32")
+    assert torch.equal(hotpath.query_sdf(ctx1, kw, one.points), a[1:])
+
+
+def test_edge_sizes():
+    inp = synth.make_inputs(seed=11, B=1, N=300, size="small")
+    g = inp.to(DEV)
+    for mode in ("fp32", "bf16"):
+        ctx, kw = ctx_and_weights(g, mode)
+        full = hotpath.query_sdf(ctx, kw, g.points)
+        assert hotpath.query_sdf(ctx, kw, g.points[:, :0]).shape == (1, 0)
+        for n in (1, 31, 33, 129, 257):
+            assert torch.equal(hotpath.query_sdf(ctx, kw, g.points[:, :n].contiguous()), full[:, :n])
+
+
+def test_full_size_256_grid_slab_properties():
+    """BASELINE.json's full size (256^3 over the full-size feature tensors) through size-independent
+    properties: a z-run of the grid evaluated by the grid kernel equals the explicit-point path, and
+    fp32 and bf16 agree within the bf16 tolerance."""
+    inp = synth.make_inputs(seed=333, B=1, N=8, size="full", trans="camera")
+    g = inp.to(DEV)
+    res = 256
+    begin, count = (128 * res + 77) * res, 3 * res + 11           # crosses z-run boundaries
+    out = {}
+    for mode in ("fp32", "bf16"):
+        ctx, kw = ctx_and_weights(g, mode)
+        a = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0)
+        pts = hotpath.grid_points(res, begin, count).unsqueeze(0)
+        b = hotpath.query_sdf(ctx, kw, pts, out_div=10.0)
+        assert torch.equal(a, b)
+        out[mode] = a
+    with torch.no_grad():
+        ref = P.list_query(inp.maps, inp.vols, inp.trans_mat, hotpath.grid_points(res, begin, count).cpu().unsqueeze(0),
+                           inp.weights) / 10.0
+    assert (out["fp32"].cpu() - ref).abs().max().item() <= FP32_TOL
+    assert (out["bf16"].cpu() - ref).abs().max().item() <= BF16_TOL
+
+
+# ------------------------------------------------------------------ backward (a-9)
+def test_backward_vs_reference_golden():
+    z = np.load(os.path.join(GOLDEN, "grad_small_b2.npz"))
+    kw_ = json.loads(str(z["recipe"]))
+    inp = synth.make_inputs(**kw_)
+    _, sdf_gt = synth.training_points(kw_["B"], kw_["N"], torch.Generator().manual_seed(kw_["seed"] + 1000))
+    g = inp.to(DEV)
+    maps = [m.clone().requires_grad_(True) for m in g.maps]
+    vols = [v.clone().requires_grad_(True) for v in g.vols]
+    T = g.trans_mat.clone().requires_grad_(True)
+    w = {k: v.clone().requires_grad_(True) for k, v in g.weights.items()}
+    ups = [torch.nn.functional.interpolate(m, size=137, mode="bilinear", align_corners=True) for m in maps]
+    maps_cl = torch.cat(ups, dim=1).permute(0, 2, 3, 1).contiguous()
+    vols_cl = [v.permute(0, 2, 3, 4, 1).contiguous() for v in vols]
+    sdf = hotpath.query_sdf_autograd(g.points, T, maps_cl, vols_cl, w, raw=True)
+    assert np.abs(sdf.detach().cpu().numpy() - z["sdf"]).max() <= FP32_TOL
+    loss = ((sdf_gt.to(DEV) * float(z["sdf_scale"]) - sdf) ** 2).sum(-1).mean()
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) <= 1e-4 * abs(float(z["loss"]))
+
+    def rel(a, b):
+        a = a.detach().cpu().numpy()
+        return np.abs(a - b).max() / (np.abs(b).max() + 1e-12)
+    tol = 1e-3                                              # grads rel-err <= 1e-3 fp32
+    assert rel(T.grad, z["dT"]) <= tol
+    for key, p_ in w.items():                             # every MLP weight and bias
+        gflat = p_.grad.flatten()
+        if gflat.numel() > 70000:
+            gflat = gflat[::97]                              # make_golden.py stores a strided subsample
+        assert rel(gflat, z["dW_" + key.replace(".", "_")].reshape(-1)) <= tol, key
+    for i, v in enumerate(vols):
+        assert rel(v.grad.flatten()[::7], z[f"dvol{i}_sub"]) <= tol
+        assert abs(v.grad.double().sum().item() - float(z[f"dvol{i}_sum"])) <= 1e-3 * (abs(float(z[f"dvol{i}_sum"])) + 1)
+    for i, m in enumerate(maps):
+        assert rel(m.grad.flatten()[::13], z[f"dmap{i}_sub"]) <= tol

@@ -1,0 +1,63 @@
+"""CPU tests of the N>1 path: shard arithmetic and the single gather, with
+world_size-2 gloo processes."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from list_b200 import parallel
+
+
+def test_shard_range_covers_exactly():
+    for total in (0, 1, 7, 64 ** 3, 256 ** 3, 1000):
+        for world in (1, 2, 3, 4, 8):
+            for align in (1, 64, 65536):
+                spans = [parallel.shard_range(total, r, world, align) for r in range(world)]
+                pos = 0
+                for b, c in spans:
+                    assert b == min(pos, total) and c >= 0
+                    pos = b + c
+                assert pos == total
+                assert all(b % align == 0 for b, c in spans if c > 0)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, total, align, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        def evaluate(begin, count):          # stands in for the per-rank kernel launch
+            idx = torch.arange(begin, begin + count, dtype=torch.float32)
+            return torch.stack([idx * 2 + 1, -idx])
+        out = parallel.sharded_grid(evaluate, total, align)
+        ref = torch.arange(total, dtype=torch.float32)
+        ok = torch.equal(out, torch.stack([ref * 2 + 1, -ref]))
+        q.put((rank, bool(ok), tuple(out.shape)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total,align", [(4096, 256), (1000, 1), (27, 9)])
+def test_sharded_grid_gloo_world2(total, align):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, total, align, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(ok for _, ok, _ in res), res
+    assert all(shape == (2, total) for _, _, shape in res)
