@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- SDF queries/sec of the LIST per-query hot path on a dense res^3 grid per image
+(BASELINE.json metric; cfg-4: 1 image, 256^3 grid, sharded by point ranges across N B200s with one
+NCCL gather).
+
+    python bench.py [--gpus N --steps K --warmup W] [--impl reference]
+
+A "step" = one pass of the hot path (fused gather + implicit MLP, every chunk) over the whole
+grid of one synthetic image.  One JSON line is printed by rank 0 (see the keys at the bottom).
+`--impl reference` times the reference's own CPU implementation of the path (the ATen-op port in
+oracle/ref_port.py -- the Python reference cannot travel to the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_QUERY = 4_090_368            # MLP MACs*2, K = 3610 unpadded
+METRIC = "sdf_queries_per_sec"
+UNIT = "queries/s"
+SDF_SCALE = 10.0
+CPU_CHUNK = 65536                     # reference arguments.py:18
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--res", type=int, default=256)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--chunk", type=int, default=262144)
+    ap.add_argument("--cpu-chunks", type=int, default=2, help="65536-point chunks timed for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor": p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                "tensor_burst": p["bf16_tflops"], "src": "measured (MEASURED_PEAKS.json; tensor = sustained figure, "
+                "the kernel is timed inside a long step)"}
+    return {"hbm": 6650.0, "tensor": 1400.0, "tensor_burst": 1590.0, "src": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=lambda: [self.lines.append(l) for l in self.proc.stdout], daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(res: int, chunks: int, warm: int = 0):
+    """Times the reference's CPU path (ATen-op port, all host threads) on `chunks` 65536-point chunks of
+    the same grid / same synthetic image.  Returns (queries/s, cores, sample description)."""
+    import torch
+    from list_b200 import synth
+    from oracle import ref_port
+    from oracle.list_oracle import create_grid_points_from_bounds
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")
+    grid = torch.tensor(create_grid_points_from_bounds(-0.5, 0.5, res)[: (chunks + warm) * CPU_CHUNK]).unsqueeze(0).float()
+    parts = torch.split(grid, CPU_CHUNK, 1)
+    with torch.no_grad():
+        for p in parts[:warm]:
+            ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
+        t0 = time.perf_counter()
+        n = 0
+        for p in parts[warm:warm + chunks]:
+            ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
+            n += p.shape[1]
+        dt = time.perf_counter() - t0
+    return n / dt, cores, f"first {chunks} x {CPU_CHUNK}-point chunks of the {res}^3 grid, fp32, torch CPU {cores} threads"
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from list_b200 import synth
+    from oracle import ref_port
+    from oracle.list_oracle import create_grid_points_from_bounds
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    inp = synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")
+    n_chunks = a.steps + a.warmup
+    grid = torch.tensor(create_grid_points_from_bounds(-0.5, 0.5, a.res)[: n_chunks * CPU_CHUNK]).unsqueeze(0).float()
+    parts = torch.split(grid, CPU_CHUNK, 1)
+    with torch.no_grad():
+        for p in parts[:a.warmup]:
+            ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
+        t0 = time.perf_counter()
+        for p in parts[a.warmup:]:
+            ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
+        dt = time.perf_counter() - t0
+    value = a.steps * CPU_CHUNK / dt
+    sample = f"each step = one {CPU_CHUNK}-point chunk of the {a.res}^3 grid (reference executors.py:215-224), fp32"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": dt / a.steps * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg-4: 1 image, {a.res}^3 dense SDF grid, bounded sample per step", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference(a)
+
+    import torch
+    import torch.distributed as dist
+    from list_b200 import hotpath, parallel, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    res, total = a.res, a.res ** 3
+    inp = synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")   # same image on every rank
+    g = inp.to(dev)
+    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, a.dtype)
+    kw = hotpath.prepare_weights(g.weights, ctx.layout, a.dtype)
+    lay = ctx.layout
+    begin, count = parallel.shard_range(total, rank, world, align=res * res)
+    chunk = max(1, min(a.chunk, count))
+    cs, wsn = ctx.struct(), kw.struct()
+    ws = hotpath._workspace(cs, wsn, chunk, dev)
+    local_out = torch.empty(1, count, device=dev, dtype=torch.float32)
+    n_chunks = -(-count // chunk)
+
+    def step():
+        hotpath.grid_sdf(ctx, kw, res, begin, count, SDF_SCALE, chunk, out=local_out, workspace=ws)
+        if world > 1:
+            return parallel.gather_shards(local_out, total, world, align=res * res)
+        return local_out
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    sync()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    for _ in range(a.steps):
+        full = step()
+    e1.record()
+    sync()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = ms.item()
+    value = total * a.steps / (ms_total * 1e-3)
+    checksum = float(full.double().sum().item())
+
+    # ---- per-kernel timing for the roofline (same stream, CUDA events, after the timed region) ----
+    t_gather = t_mlp = 0.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    for rep in range(2):                                   # rep 0 warms the allocator
+        tg = tm = 0.0
+        for n0 in range(0, count, chunk):
+            n = min(chunk, count - n0)
+            ev[0].record()
+            X = hotpath.gather_grid_features(ctx, 0, res, begin + n0, n)
+            ev[1].record()
+            hotpath.mlp(kw, X, SDF_SCALE)
+            ev[2].record()
+            torch.cuda.synchronize()
+            tg += ev[0].elapsed_time(ev[1])
+            tm += ev[1].elapsed_time(ev[2])
+            del X
+        t_gather, t_mlp = tg, tm
+    pk = peaks()
+    es = 2 if a.dtype == "bf16" else 4
+    mlp_tflops = FLOP_PER_QUERY * count / (t_mlp * 1e-3) / 1e12
+    feat_bytes = sum(t.numel() * t.element_size() for t in [ctx.maps_cl, *ctx.vols_cl])
+    gather_bytes = count * lay.k_out * es + feat_bytes               # SURVEY.md §8d (q is generated in-kernel)
+    gather_gbs = gather_bytes / (t_gather * 1e-3) / 1e9
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
+    roof_mlp = {"kernel": "mlp_tc_kernel" if a.dtype == "bf16" else "sgemm_kernel", "bound": "tensor",
+                "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
+                "traffic": traffic.get("mlp"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
+                "peak_source": pk["src"]}
+    roof_gather = {"kernel": "gather_fwd_kernel", "bound": "hbm", "achieved": gather_gbs, "peak": pk["hbm"],
+                   "unit": "GB/s", "frac": gather_gbs / pk["hbm"], "traffic": traffic.get("gather"),
+                   "ms_per_step": t_gather, "launches_per_step": n_chunks, "peak_source": pk["src"]}
+    dominant, other = (roof_mlp, roof_gather) if t_mlp >= t_gather else (roof_gather, roof_mlp)
+
+    # ---- end to end through the C ABI with HOST buffers (H2D + prep + grid + D2H inside the timed region) ----
+    e2e = None
+    if not a.no_e2e:
+        pin = lambda t: t.contiguous().pin_memory()
+        runner = hotpath.HostGridRunner([pin(m) for m in inp.maps], [pin(v) for v in inp.vols], pin(inp.trans_mat), kw,
+                                        res, begin, count, a.dtype, chunk)
+        for _ in range(2):
+            runner.run(SDF_SCALE)
+        sync()
+        e_steps = min(a.steps, 3)
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            host_out = runner.run(SDF_SCALE)
+            torch.cuda.synchronize()                      # the D2H result is consumed every step
+            _ = float(host_out[0, 0])
+        sync()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": total * e_steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
+               "d2h_bytes_per_step": runner.d2h_bytes, "steps": e_steps,
+               "what": "list_sdf_grid_host: pinned host per-image tensors -> H2D -> prep kernels -> gather+MLP over "
+                       "the rank's grid shard -> D2H of its SDF values; max over ranks"}
+        # sanity: same numbers as the resident path
+        assert torch.equal(host_out, local_out.cpu()), "host path and resident path disagree"
+
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v, cores, sample = cpu_reference_rate(res, a.cpu_chunks)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": f"cfg-4: LIST inference, 1 image (224x224 synthetic features), {res}^3 dense SDF grid "
+                                   f"sharded by contiguous point ranges over {world} GPU(s) + one NCCL all_gather",
+                       "grid_res": res, "queries_per_step": total, "chunk_rows": chunk, "sdf_scale": SDF_SCALE,
+                       "trans_mat": "camera-like", "mlp_variant": os.environ.get("LIST_B200_MLP_VARIANT", "2"),
+                       "l2": "no flush: every step streams 2 x rows x 7296 B of feature rows (>> 126 MB L2) plus "
+                             "132 MB of per-image tensors",
+                       "parallelism": f"grid-shard x{world}"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * n_chunks * 2,
+            "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
+            "checksum": checksum,
+        }), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -157,6 +157,12 @@ LIST_API size_t list_mlp_workspace_bytes(const ListWeights* w, int64_t rows);
 LIST_API int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf,
                  float out_div, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Diagnostic twin of list_mlp_fwd for the bf16 tensor-core kernel: additionally copies the hidden
+ * activations relu(fc_0) [rows][n0], relu(fc_1) [rows][n1], relu(fc_2) [rows][n2] (fp32, before the
+ * bf16 rounding the next layer sees) into h1/h2/h3 (each may be NULL) for layer-wise parity tests. */
+LIST_API int list_mlp_fwd_debug(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf,
+                       float out_div, float* h1, float* h2, float* h3, void* stream);
+
 /* a-7: gather + MLP for explicit query points, chunked through `workspace`. */
 LIST_API size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_t chunk_rows);
 LIST_API int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw,

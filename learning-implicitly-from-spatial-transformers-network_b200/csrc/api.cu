@@ -39,7 +39,7 @@ int mlp_f32_bwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows,
 int gather_bwd(const ListCtx* ctx, const float* q, int q_is_raw, int B, int64_t N, const float* dX, int64_t ldd,
                const ListGrads* g, cudaStream_t st);
 int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
-               cudaStream_t st);
+               float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
 
 static size_t elem_size(int dtype) { return dtype == LIST_BF16 ? 2 : 4; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -224,7 +224,17 @@ int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows,
     }
     return mlp_f32_fwd(w, static_cast<const float*>(X), ldx, rows, sdf, out_div, static_cast<float*>(workspace), st);
   }
-  return mlp_tc_fwd(w, X, ldx, rows, sdf, out_div, mlp_variant(), st);
+  return mlp_tc_fwd(w, X, ldx, rows, sdf, out_div, mlp_variant(), nullptr, nullptr, nullptr, st);
+}
+
+int list_mlp_fwd_debug(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div,
+                       float* h1, float* h2, float* h3, void* stream) {
+  int rc = check_weights(w, -1);
+  if (rc) return rc;
+  LIST_CHECK_ARG(w->dtype == LIST_BF16, "list_mlp_fwd_debug: bf16 tensor-core kernel only");
+  LIST_CHECK_ARG(rows >= 1 && X && sdf && out_div != 0.f, "list_mlp_fwd_debug: bad arguments");
+  LIST_CHECK_ARG(ldx >= w->k_pad && ldx % 8 == 0, "list_mlp_fwd_debug: bad ldx %lld", (long long)ldx);
+  return mlp_tc_fwd(w, X, ldx, rows, sdf, out_div, mlp_variant(), h1, h2, h3, static_cast<cudaStream_t>(stream));
 }
 
 size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_t chunk_rows) {

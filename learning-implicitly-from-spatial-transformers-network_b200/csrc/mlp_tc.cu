@@ -213,7 +213,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
               const float* __restrict__ b0, const float* __restrict__ b1, const float* __restrict__ b2,
               const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ sdf,
-              long long rows, int nk0, float out_div) {
+              long long rows, int nk0, float out_div, float* __restrict__ dbg1, float* __restrict__ dbg2,
+              float* __restrict__ dbg3) {
   using C = Cfg<CG>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -383,6 +384,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                              fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
         }
         tmem_st16(tq + j * 16, u);
+        if (dbg1 != nullptr && row < rows) {               // diagnostic copy of relu(fc_0) (fp32, pre-rounding)
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            dbg1[row * N0 + j * 32 + i] = fmaxf(__uint_as_float(v[i]) + s_b0[j * 32 + i], 0.f);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -402,6 +408,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
                              fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
         }
         tmem_st16(tq + j * 16, u);
+        if (dbg2 != nullptr && row < rows) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            dbg2[row * N1 + j * 32 + i] = fmaxf(__uint_as_float(v[i]) + s_b1[j * 32 + i], 0.f);
+        }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -418,6 +429,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 32; ++i)
           acc = fmaf(fmaxf(__uint_as_float(v[i]) + s_b2[j * 32 + i], 0.f), s_w3[j * 32 + i], acc);
+        if (dbg3 != nullptr && row < rows) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            dbg3[row * N2 + j * 32 + i] = fmaxf(__uint_as_float(v[i]) + s_b2[j * 32 + i], 0.f);
+        }
       }
       tc_fence_before();
       if (CG == 2) mbar_arrive_cluster(hready_remote);
@@ -468,7 +484,7 @@ static int make_map(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t ou
 
 template <int CG>
 static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div,
-                  cudaStream_t st) {
+                  float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
   using C = Cfg<CG>;
   CUtensorMap tmX, tmW0, tmW1, tmW2;
   int rc;
@@ -497,7 +513,7 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   cfg.numAttrs = 1;
   const int nk0 = w->k_pad / BK;
   LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
-                               sdf, static_cast<long long>(rows), nk0, out_div));
+                               sdf, static_cast<long long>(rows), nk0, out_div, dbg1, dbg2, dbg3));
   return LIST_OK;
 }
 
@@ -505,7 +521,7 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
 
 // variant: 1 = single-CTA tcgen05 (cta_group::1), 2 = CTA pair (cta_group::2)
 int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
-               cudaStream_t st) {
+               float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
   if (rows == 0) return LIST_OK;
   LIST_CHECK_ARG(w->n0 == tc::N0 && w->n1 == tc::N1 && w->n2 == tc::N2,
                  "mlp_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
@@ -513,8 +529,8 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
   LIST_CHECK_ARG(ldx % 8 == 0 && ldx >= w->k_pad, "mlp_tc: ldx %lld must be >= k_pad and a multiple of 8", (long long)ldx);
   LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "mlp_tc: X must be 16-byte aligned");
   LIST_CHECK_ARG(rows < (1LL << 31), "mlp_tc: rows %lld too large for one call", (long long)rows);
-  if (variant == 1) return tc::launch<1>(w, X, ldx, rows, sdf, out_div, st);
-  return tc::launch<2>(w, X, ldx, rows, sdf, out_div, st);
+  if (variant == 1) return tc::launch<1>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, st);
+  return tc::launch<2>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, st);
 }
 
 }  // namespace list

@@ -409,3 +409,18 @@ def query_sdf_autograd(points, trans_mat, maps_cl, vols_cl, params: dict, raw: b
                               p[f"{prefix}fc_0.weight"], p[f"{prefix}fc_0.bias"], p[f"{prefix}fc_1.weight"],
                               p[f"{prefix}fc_1.bias"], p[f"{prefix}fc_2.weight"], p[f"{prefix}fc_2.bias"],
                               p[f"{prefix}fc_out.weight"], p[f"{prefix}fc_out.bias"], *vols_cl)
+
+
+def mlp_debug(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0):
+    """Diagnostic: bf16 tensor-core MLP returning (sdf, relu(fc_0), relu(fc_1), relu(fc_2)) in fp32."""
+    dev = _require_cuda(X, weights.w0)
+    rows = X.shape[0]
+    sdf = torch.empty(rows, device=dev, dtype=torch.float32)
+    h1 = torch.zeros(rows, weights.w0.shape[0], device=dev, dtype=torch.float32)
+    h2 = torch.zeros(rows, weights.w1.shape[0], device=dev, dtype=torch.float32)
+    h3 = torch.zeros(rows, weights.w2.shape[0], device=dev, dtype=torch.float32)
+    ws = weights.struct()
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().list_mlp_fwd_debug(C.byref(ws), X.data_ptr(), X.stride(0), rows, sdf.data_ptr(), float(out_div),
+                                             h1.data_ptr(), h2.data_ptr(), h3.data_ptr(), _stream()), "list_mlp_fwd_debug")
+    return sdf, h1, h2, h3

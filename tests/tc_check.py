@@ -12,13 +12,14 @@ sys.path.insert(0, ROOT)
 
 
 def reference(X, kw):
-    """bf16 operands, fp32 accumulation, hidden activations rounded to bf16 (what the kernel does)."""
+    """bf16 operands, fp32 accumulation, hidden activations rounded to bf16 (what the kernel does).
+    Returns (sdf, h1, h2, h3) with h* the fp32 pre-rounding activations."""
     import torch
     f = lambda t: t.float()
-    h = torch.relu(f(X) @ f(kw.w0).t() + kw.b0).bfloat16()
-    h = torch.relu(f(h) @ f(kw.w1).t() + kw.b1).bfloat16()
-    h = torch.relu(f(h) @ f(kw.w2).t() + kw.b2)
-    return h @ kw.w3 + kw.b3
+    h1 = torch.relu(f(X) @ f(kw.w0).t() + kw.b0)
+    h2 = torch.relu(f(h1.bfloat16()) @ f(kw.w1).t() + kw.b1)
+    h3 = torch.relu(f(h2.bfloat16()) @ f(kw.w2).t() + kw.b2)
+    return h3 @ kw.w3 + kw.b3, h1, h2, h3
 
 
 def main():
@@ -27,6 +28,7 @@ def main():
     ap.add_argument("--rows", type=int, default=1000)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--out-div", type=float, default=1.0)
+    ap.add_argument("--layers", action="store_true", help="also check the hidden activations layer by layer")
     a = ap.parse_args()
     os.environ["LIST_B200_MLP_VARIANT"] = str(a.variant)
     import torch
@@ -44,10 +46,18 @@ def main():
     X = X.to(dev).bfloat16()
     out = hotpath.mlp(kw, X, a.out_div)
     torch.cuda.synchronize()
-    ref = reference(X, kw) / a.out_div
+    ref, r1, r2, r3 = reference(X, kw)
+    ref = ref / a.out_div
     err = (out - ref).abs().max().item()
-    print(json.dumps({"variant": a.variant, "rows": a.rows, "max_err": err, "ref_absmax": ref.abs().max().item(),
-                      "finite": bool(torch.isfinite(out).all().item())}))
+    res = {"variant": a.variant, "rows": a.rows, "max_err": err, "ref_absmax": ref.abs().max().item(),
+           "finite": bool(torch.isfinite(out).all().item())}
+    if a.layers:
+        out2, h1, h2, h3 = hotpath.mlp_debug(kw, X, a.out_div)
+        torch.cuda.synchronize()
+        res.update({"h1_err": (h1 - r1).abs().max().item(), "h2_err": (h2 - r2).abs().max().item(),
+                    "h3_err": (h3 - r3).abs().max().item(), "h1_absmax": r1.abs().max().item(),
+                    "debug_equals_plain": bool(torch.equal(out, out2))})
+    print(json.dumps(res))
 
 
 if __name__ == "__main__":
