@@ -248,7 +248,8 @@ def main():
                 "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
                 "traffic": traffic.get("mlp"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
                 "peak_source": pk["src"]}
-    roof_gather = {"kernel": "gather_fwd_kernel", "bound": "hbm", "achieved": gather_gbs, "peak": pk["hbm"],
+    generic = os.environ.get("LIST_B200_GRID_GENERIC", "0") == "1"
+    roof_gather = {"kernel": "gather_fwd_kernel" if generic else "gather_grid_kernel", "bound": "hbm", "achieved": gather_gbs, "peak": pk["hbm"],
                    "unit": "GB/s", "frac": gather_gbs / pk["hbm"], "traffic": traffic.get("gather"),
                    "ms_per_step": t_gather, "launches_per_step": n_chunks, "peak_source": pk["src"]}
     dominant, other = (roof_mlp, roof_gather) if t_mlp >= t_gather else (roof_gather, roof_mlp)

@@ -29,6 +29,8 @@ int prep_volume(const float* in, int B, int C, int R, void* out, int dtype, cuda
 int gather_fwd(const ListCtx* ctx, const float* q, int q_is_raw, void* X, int64_t ldx, int B, int64_t N, cudaStream_t st);
 int gather_grid_fwd(const ListCtx* ctx, int image, int res, double bb_min, double bb_max, int64_t begin, int64_t count,
                     void* X, int64_t ldx, cudaStream_t st);
+int gather_grid_walk(const ListCtx* ctx, int image, int res, double bb_min, double bb_max, int64_t begin, int64_t count,
+                     void* X, int64_t ldx, cudaStream_t st);
 int grid_points(float* q, int res, double lo, double hi, int64_t begin, int64_t count, cudaStream_t st);
 size_t mlp_f32_workspace_bytes(const ListWeights* w, int64_t rows);
 int mlp_f32_fwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows, float* sdf, float out_div, float* ws,
@@ -73,6 +75,18 @@ static int check_weights(const ListWeights* w, int k_pad) {
   LIST_CHECK_ARG(((reinterpret_cast<uintptr_t>(w->w0) | reinterpret_cast<uintptr_t>(w->w1) |
                    reinterpret_cast<uintptr_t>(w->w2)) & 15) == 0, "weight matrices must be 16B aligned");
   return LIST_OK;
+}
+
+// Dense-grid gather: the z-run walker kernel (gather_grid.cu); configurations it does not cover, or
+// LIST_B200_GRID_GENERIC=1 (A/B aid), use the generic per-point kernel in grid mode.
+static int grid_gather(const ListCtx* ctx, int image, int res, double bb_min, double bb_max, int64_t begin, int64_t count,
+                       void* X, int64_t ldx, cudaStream_t st) {
+  const char* e = getenv("LIST_B200_GRID_GENERIC");
+  if (!(e && e[0] == '1')) {
+    const int rc = gather_grid_walk(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, st);
+    if (rc != LIST_ENOSYS) return rc;
+  }
+  return gather_grid_fwd(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, st);
 }
 
 static int mlp_variant() {
@@ -197,7 +211,7 @@ int list_gather_grid_fwd(const ListCtx* ctx, int32_t image, int32_t res, double 
   if ((rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr))) return rc;
   LIST_CHECK_ARG(X != nullptr && ldx >= lay.k_pad && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
                  "list_gather_grid_fwd: X NULL/unaligned or ldx %lld < %d", (long long)ldx, lay.k_pad);
-  return gather_grid_fwd(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, static_cast<cudaStream_t>(stream));
+  return grid_gather(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, static_cast<cudaStream_t>(stream));
 }
 
 size_t list_mlp_workspace_bytes(const ListWeights* w, int64_t rows) {
@@ -314,7 +328,7 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
   for (int b = 0; b < ctx->B; ++b) {
     for (int64_t n0 = 0; n0 < count; n0 += chunk_rows) {
       const int64_t n = (count - n0 < chunk_rows) ? (count - n0) : chunk_rows;
-      if ((rc = gather_grid_fwd(ctx, b, res, bb_min, bb_max, begin + n0, n, X, lay.k_pad, st))) return rc;
+      if ((rc = grid_gather(ctx, b, res, bb_min, bb_max, begin + n0, n, X, lay.k_pad, st))) return rc;
       if ((rc = list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, mlp_ws,
                              workspace_bytes - xb, stream)))
         return rc;

@@ -158,22 +158,41 @@ def test_dense_grid_32_vs_oracle_and_sign_pattern():
 
 
 @pytest.mark.parametrize("mode", ["fp32", "bf16"])
-def test_grid_kernel_equals_explicit_points_and_shards_compose(mode):
-    """gather_grid(begin,count) == gather(explicit grid points), and a grid evaluated in shards /
-    chunks of any size is bit-identical to one pass (what multi-GPU sharding relies on)."""
+@pytest.mark.parametrize("res", [24, 40])
+def test_grid_kernel_vs_explicit_points_and_shards_compose(mode, res, monkeypatch):
+    """The dense-grid walker kernel equals the per-point kernel on the same grid points up to fp32
+    re-association (it evaluates the trilinear sum separably along z-runs), the generic kernel in grid
+    mode equals it bit for bit, and a grid evaluated in shards / chunks of any size is bit-identical to
+    one pass (what multi-GPU sharding relies on)."""
     inp = synth.make_inputs(seed=9, B=2, N=8, size="small", trans="random")
     g = inp.to(DEV)
     ctx, kw = ctx_and_weights(g, mode)
-    res = 24
     total = res ** 3
     whole = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=total)
     pts = hotpath.grid_points(res).unsqueeze(0).expand(2, -1, -1).contiguous()
     explicit = hotpath.query_sdf(ctx, kw, pts, out_div=10.0, chunk_rows=4096)
-    assert torch.equal(whole, explicit)
+    tol = 2e-6 if mode == "fp32" else 1e-3          # bf16: a re-associated feature may round to the other bf16 neighbour
+    assert (whole - explicit).abs().max().item() <= tol
     parts = []
     for begin, count in ((0, 1000), (1000, 5000), (6000, total - 6000)):
         parts.append(hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=777))
     assert torch.equal(torch.cat(parts, dim=1), whole)
+    monkeypatch.setenv("LIST_B200_GRID_GENERIC", "1")
+    generic = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=3000)
+    assert torch.equal(generic, explicit)
+
+
+def test_grid_walker_rows_match_generic_rows():
+    """Feature rows of the walker kernel against the per-point kernel, column by column."""
+    inp = synth.make_inputs(seed=12, B=1, N=8, size="small", trans="camera")
+    g = inp.to(DEV)
+    for mode, tol in (("fp32", 5e-6), ("bf16", 0.04)):
+        ctx, _ = ctx_and_weights(g, mode)
+        for res, begin, count in ((20, 0, 8000), (33, 1234, 3000), (7, 0, 343)):
+            a = hotpath.gather_grid_features(ctx, 0, res, begin, count).float()
+            b = hotpath.gather_features(ctx, hotpath.grid_points(res, begin, count).unsqueeze(0)).float()
+            assert a.shape == b.shape
+            assert (a - b).abs().max().item() <= tol, (mode, res, (a - b).abs().max().item())
 
 
 def test_point_permutation_and_batch_independence():
@@ -215,7 +234,7 @@ def test_full_size_256_grid_slab_properties():
         a = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0)
         pts = hotpath.grid_points(res, begin, count).unsqueeze(0)
         b = hotpath.query_sdf(ctx, kw, pts, out_div=10.0)
-        assert torch.equal(a, b)
+        assert (a - b).abs().max().item() <= (2e-6 if mode == "fp32" else 1e-3)
         out[mode] = a
     with torch.no_grad():
         ref = P.list_query(inp.maps, inp.vols, inp.trans_mat, hotpath.grid_points(res, begin, count).cpu().unsqueeze(0),
