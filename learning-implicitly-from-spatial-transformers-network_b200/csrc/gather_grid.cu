@@ -5,25 +5,35 @@
 // z-runs with fixed (x, y).  In the swapped/scaled frame only the W coordinate of the voxel taps
 // changes along a run, the (H, D) corners and their weights are constant.  A thread therefore
 // owns one 8-channel vector of one (level, displacement) pair and WALKS the run:
-//     G[xv] = sum over the 4 (H,D) corners of (wy*wz) * V[z_k][y_k][xv][c..c+8)   (kept in registers
-//             for xv = x0 and x1; when x0 advances, G0 <- G1 and only ONE new row is fetched)
-//     out   = wx0 * G[x0] + wx1 * G[x1]
+//     G[xv] = sum over the 4 (H,D) corners of (wy*wz) * V[z_k][y_k][xv][c..c+8)   (in registers for
+//             xv = x0 and x1; when x0 advances, G0 <- G1 and only ONE new row is fetched)
+//     out   = G0 + wx1 * (G1 - G0)
 // i.e. the trilinear sum evaluated separably.  That cuts the 56 tap reads per (point, level,
-// channel vector) of the generic kernel to ~4*R/res per step, and the FMAs from 8 to 2 + 4*R/res.
+// channel vector) of the generic kernel to ~4*R/res per step and the FMAs from 56 to ~1 + 4*R/res.
 // The 2-D taps are cached the same way (the pixel cell changes every ~2-3 steps at 256^3).
 // Results differ from the generic kernel only by fp32 re-association (~1e-7 relative); a point's
-// value does not depend on how the grid is chunked or sharded (bit-exact composition).
+// value never depends on how the grid is chunked or sharded (bit-exact composition).
 //
-// Mapping: CTA = kPz consecutive grid points, 512 threads:
-//   threads [0, Cm/8)            2-D walkers (one 8-channel vector each)
-//   next 7*sum(C/8) threads      3-D vector walkers, ordered (level, d in {0,3,4,5,6,1,2}, cv) so that
-//                                lanes of a warp mostly change cell at the same step
-//   last warp                    scalar levels (the 1-channel occupancy volume), q and the zero pad
-// Every step each walker stores its 16 B piece of the point's row, so a row is written as
-// contiguous segments by neighbouring lanes.
+// Mapping: grid = (ceil(N/64), roles), 128 threads.  blockIdx.y selects a ROLE -- a group of walkers
+// with similar cost (the 2-D vectors; one or more voxel levels; the scalar tail) -- so every CTA is
+// homogeneous, finishes on its own, and the hardware scheduler balances the roles.  Per-step
+// coordinates (voxel index + weight per level and W-shift class; pixel cell + 4 weights) are
+// computed once per point in phase 0 and shared through shared memory.
 #include "common.cuh"
 
 namespace list {
+
+constexpr int kPz = 64;            // points per CTA
+constexpr int kRoleThreads = 128;
+constexpr int kMaxRoles = 12;
+constexpr int kRoleLevels = 4;     // voxel levels one role may span
+
+struct GridRole {
+  int kind;                        // 0 = 2-D vectors, 1 = 3-D vectors, 2 = scalar tail
+  int first, count;                // 2-D: channel-vector range; 3-D: item range in layout order
+  int nlev;                        // 3-D: levels touched (for the phase-0 tables)
+  int lev[kRoleLevels];
+};
 
 struct GridGatherParams {
   const void* maps;
@@ -39,15 +49,14 @@ struct GridGatherParams {
   int map_off, xyz_off, k_pad, tail0;
   int res;
   double bb_min, bb_max;
-  int n2d, n3d;          // walker counts
+  int nroles;
+  GridRole roles[kMaxRoles];
 };
-
-constexpr int kPz = 64;
-constexpr int kGridThreads = 512;
 
 __device__ __forceinline__ int disp_order(int i) {   // W-shifted displacements (1,2) last
   return i == 0 ? 0 : (i <= 4 ? i + 2 : i - 4);
 }
+__device__ __forceinline__ int shift_class(int d) { return d == 1 ? 1 : (d == 2 ? 2 : 0); }
 
 template <typename T>
 __device__ __forceinline__ void load_row8(const T* __restrict__ vol, const uint32_t base[4], const float wyz[4],
@@ -64,17 +73,22 @@ __device__ __forceinline__ void load_row8(const T* __restrict__ vol, const uint3
   }
 }
 
+struct AxEntry { int i0; float w1; };          // voxel index along W and the weight of i0+1
+struct UvEntry { int x0, y0; float w00, w01, w10, w11; };
+
 template <typename T>
-__global__ void __launch_bounds__(kGridThreads) gather_grid_kernel(const GridGatherParams p) {
+__global__ void __launch_bounds__(kRoleThreads) gather_grid_kernel(const GridGatherParams p) {
   __shared__ float s_q[kPz][3];
-  __shared__ float s_uv[kPz][2];
   __shared__ int s_new[kPz];
+  __shared__ AxEntry s_ax[kRoleLevels][3][kPz];
+  __shared__ UvEntry s_uv[kPz];
   const int tid = threadIdx.x;
+  const GridRole& role = p.roles[blockIdx.y];
   const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kPz;
   const int npts = static_cast<int>(min64(kPz, p.N - n0));
   T* __restrict__ Xb = static_cast<T*>(p.X) + n0 * p.ldx;
 
-  // ---- phase 0: grid index -> point (numpy linspace semantics), swap/scale, 2-D sample position ----
+  // ---- phase 0a: grid index -> point (numpy linspace semantics), swap/scale ----
   if (tid < kPz) {
     float q[3] = {0.f, 0.f, 0.f};
     int fresh = 1;
@@ -88,50 +102,69 @@ __global__ void __launch_bounds__(kGridThreads) gather_grid_kernel(const GridGat
       q[0] = rz * 2.0f; q[1] = ry * 2.0f; q[2] = rx * 2.0f;   // reference models.py:91-92
       fresh = (tid == 0 || gz == 0) ? 1 : 0;
     }
-    float ix, iy, h[3];
-    localise(q, p.T, p.S, ix, iy, h);
     s_q[tid][0] = q[0]; s_q[tid][1] = q[1]; s_q[tid][2] = q[2];
-    s_uv[tid][0] = ix; s_uv[tid][1] = iy;
     s_new[tid] = fresh;
+    if (role.kind == 0) {                                       // 2-D sample position and tap weights
+      float ix, iy, h[3];
+      localise(q, p.T, p.S, ix, iy, h);
+      UvEntry e{0, 0, 0.f, 0.f, 0.f, 0.f};                      // NaN grid -> all taps out of bounds
+      if (ix == ix && iy == iy) {
+        const float fx = floorf(ix), fy = floorf(iy);
+        e.x0 = static_cast<int>(fx); e.y0 = static_cast<int>(fy);
+        const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+        const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+        const bool okx1 = (e.x0 + 1) <= p.S - 1, oky1 = (e.y0 + 1) <= p.S - 1;
+        e.w00 = wx0 * wy0;
+        e.w01 = okx1 ? wx1 * wy0 : 0.f;
+        e.w10 = oky1 ? wx0 * wy1 : 0.f;
+        e.w11 = (okx1 && oky1) ? wx1 * wy1 : 0.f;
+      }
+      s_uv[tid] = e;
+    }
   }
   __syncthreads();
+  // ---- phase 0b: per (level, W-shift class, point) voxel index and weight ----
+  if (role.kind != 0) {
+    for (int i = tid; i < role.nlev * 3 * kPz; i += kRoleThreads) {
+      const int s = i % kPz, cls = (i / kPz) % 3, li = i / (3 * kPz);
+      const float shift = cls == 0 ? 0.f : (cls == 1 ? -kDisplacement : kDisplacement);
+      const float c = cls == 0 ? s_q[s][0] : s_q[s][0] + shift;
+      const Axis3 ax = axis_border(c, p.R[role.lev[li]]);
+      s_ax[li][cls][s] = AxEntry{ax.i0, ax.w1};
+    }
+    __syncthreads();
+  }
 
-  if (tid < p.n2d) {
+  if (role.kind == 0) {
     // ================= 2-D walker: bilinear, zeros padding, cell cache =================
-    const int cv = tid;
-    const T* __restrict__ maps = static_cast<const T*>(p.maps);
+    if (tid >= role.count) return;
+    const int cv = role.first + tid;
+    const T* __restrict__ maps = static_cast<const T*>(p.maps) + cv * 8;
     const int lim = p.S - 1;
     int cx = -1, cy = -1;
     float v00[8], v01[8], v10[8], v11[8];
-    for (int s = 0; s < npts; ++s) {
-      const float ix = s_uv[s][0], iy = s_uv[s][1];
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ix == ix && iy == iy) {
-        const float fx = floorf(ix), fy = floorf(iy);
-        const int x0 = static_cast<int>(fx), y0 = static_cast<int>(fy);
-        if (x0 != cx || y0 != cy) {
-          cx = x0; cy = y0;
-          const int x1 = min(x0 + 1, lim), y1 = min(y0 + 1, lim);
-          load8(maps + (static_cast<size_t>(y0) * p.S + x0) * p.Cm + cv * 8, v00);
-          load8(maps + (static_cast<size_t>(y0) * p.S + x1) * p.Cm + cv * 8, v01);
-          load8(maps + (static_cast<size_t>(y1) * p.S + x0) * p.Cm + cv * 8, v10);
-          load8(maps + (static_cast<size_t>(y1) * p.S + x1) * p.Cm + cv * 8, v11);
-        }
-        const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
-        const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
-        const bool okx1 = (x0 + 1) <= lim, oky1 = (y0 + 1) <= lim;
-        const float w00 = wx0 * wy0, w01 = okx1 ? wx1 * wy0 : 0.f, w10 = oky1 ? wx0 * wy1 : 0.f,
-                    w11 = (okx1 && oky1) ? wx1 * wy1 : 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          acc[j] = fmaf(v11[j], w11, fmaf(v10[j], w10, fmaf(v01[j], w01, v00[j] * w00)));
+    T* __restrict__ dst = Xb + p.map_off + cv * 8;
+    for (int s = 0; s < npts; ++s, dst += p.ldx) {
+      const UvEntry e = s_uv[s];
+      if (e.x0 != cx || e.y0 != cy) {
+        cx = e.x0; cy = e.y0;
+        const int x1 = min(cx + 1, lim), y1 = min(cy + 1, lim);
+        load8(maps + (static_cast<size_t>(cy) * p.S + cx) * p.Cm, v00);
+        load8(maps + (static_cast<size_t>(cy) * p.S + x1) * p.Cm, v01);
+        load8(maps + (static_cast<size_t>(y1) * p.S + cx) * p.Cm, v10);
+        load8(maps + (static_cast<size_t>(y1) * p.S + x1) * p.Cm, v11);
       }
-      store8(Xb + static_cast<int64_t>(s) * p.ldx + p.map_off + cv * 8, acc);
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        acc[j] = fmaf(v11[j], e.w11, fmaf(v10[j], e.w10, fmaf(v01[j], e.w01, v00[j] * e.w00)));
+      store8(dst, acc);
     }
-  } else if (tid < p.n2d + p.n3d) {
+  } else if (role.kind == 1) {
     // ================= 3-D vector walker =================
-    int item = tid - p.n2d;
-    int l = -1, d = 0, cv = 0;
+    if (tid >= role.count) return;
+    int item = role.first + tid;
+    int l = -1, li = -1, d = 0, cv = 0;
     for (int ll = p.nlev - 1; ll >= 0; --ll) {        // same level order as the row layout
       if (p.C[ll] & 7) continue;
       const int cnt = LIST_NUM_DISP * (p.C[ll] >> 3);
@@ -144,58 +177,64 @@ __global__ void __launch_bounds__(kGridThreads) gather_grid_kernel(const GridGat
       }
       item -= cnt;
     }
-    if (l >= 0) {
-      const int R = p.R[l], C = p.C[l];
-      const T* __restrict__ vol = static_cast<const T*>(p.vols[l]);
-      const int col = p.voff[l] + d * C + cv * 8;
-      uint32_t base[4];
-      float wyz[4];
-      float G0[8], G1[8];
-      int cx0 = -1;
-      for (int s = 0; s < npts; ++s) {
+    if (l < 0) return;
+    for (int k = 0; k < role.nlev; ++k)
+      if (role.lev[k] == l) li = k;
+    const int R = p.R[l], C = p.C[l];
+    const T* __restrict__ vol = static_cast<const T*>(p.vols[l]);
+    const AxEntry* __restrict__ axs = s_ax[li][shift_class(d)];
+    uint32_t base[4] = {0, 0, 0, 0};
+    float wyz[4] = {0.f, 0.f, 0.f, 0.f};
+    float G0[8], G1[8], D[8];
+    int cx0 = -1;
+    T* __restrict__ dst = Xb + p.voff[l] + d * C + cv * 8;
+    for (int s = 0; s < npts; ++s, dst += p.ldx) {
+      const AxEntry e = axs[s];
+      bool reload = false;
+      if (s_new[s]) {                                  // new (x, y) run: (H, D) corners and weights
         const float q[3] = {s_q[s][0], s_q[s][1], s_q[s][2]};
         float pd[3];
         displaced(q, d, pd);
-        const Axis3 ax = axis_border(pd[0], R);
-        bool reload = false;
-        if (s_new[s]) {                                  // new (x, y) run: (H, D) corners and weights
-          const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
-          const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
-          const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
+        const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
+        const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
+        const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int tz = k >> 1, ty = k & 1;
-            base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * C + cv * 8;
-            wyz[k] = wy[ty] * wz[tz];
-          }
-          reload = true;
+        for (int k = 0; k < 4; ++k) {
+          const int tz = k >> 1, ty = k & 1;
+          base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * C + cv * 8;
+          wyz[k] = wy[ty] * wz[tz];
         }
-        if (reload || ax.i0 != cx0) {
-          if (!reload && ax.i0 == cx0 + 1) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) G0[j] = G1[j];
-          } else {
-            load_row8(vol, base, wyz, ax.i0, C, G0);
-          }
-          if (ax.i1 != ax.i0) load_row8(vol, base, wyz, ax.i1, C, G1);
-          else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) G1[j] = G0[j];
-          }
-          cx0 = ax.i0;
-        }
-        float out[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) out[j] = fmaf(G1[j], ax.w1, G0[j] * ax.w0);
-        store8(Xb + static_cast<int64_t>(s) * p.ldx + col, out);
+        reload = true;
       }
+      if (reload || e.i0 != cx0) {
+        const int i1 = min(e.i0 + 1, R - 1);
+        if (!reload && e.i0 == cx0 + 1) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) G0[j] = G1[j];
+        } else {
+          load_row8(vol, base, wyz, e.i0, C, G0);
+        }
+        if (i1 != e.i0) load_row8(vol, base, wyz, i1, C, G1);
+        else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) G1[j] = G0[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) D[j] = G1[j] - G0[j];
+        cx0 = e.i0;
+      }
+      float out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) out[j] = fmaf(D[j], e.w1, G0[j]);
+      store8(dst, out);
     }
-  } else if (tid >= kGridThreads - 32) {
-    // ================= tail warp: scalar levels, q, zero pad =================
-    const int lane = tid & 31;
+  } else {
+    // ================= tail: scalar levels, q, zero pad (one warp) =================
+    if (tid >= 32) return;
+    const int lane = tid;
     const int ntail = p.k_pad - p.tail0;               // <= 64 (checked by the launcher)
     const int nscal = p.xyz_off - p.tail0;             // scalar-level columns, <= 29
-    int l = -1, d = 0, c = 0;
+    int l = -1, li = 0, d = 0, c = 0;
     if (lane < nscal) {
       const int colabs = p.tail0 + lane;
       for (int ll = 0; ll < p.nlev; ++ll) {
@@ -203,22 +242,27 @@ __global__ void __launch_bounds__(kGridThreads) gather_grid_kernel(const GridGat
         const int rel = colabs - p.voff[ll];
         if (rel >= 0 && rel < LIST_NUM_DISP * p.C[ll]) { l = ll; d = rel / p.C[ll]; c = rel % p.C[ll]; }
       }
+      for (int k = 0; k < role.nlev; ++k)
+        if (role.lev[k] == l) li = k;
     }
     const int R = l >= 0 ? p.R[l] : 1, C = l >= 0 ? p.C[l] : 1;
     const T* __restrict__ vol = l >= 0 ? static_cast<const T*>(p.vols[l]) : nullptr;
+    const AxEntry* __restrict__ axs = s_ax[li][shift_class(d)];
     uint32_t base[4] = {0, 0, 0, 0};
     float wyz[4] = {0.f, 0.f, 0.f, 0.f};
     float g0 = 0.f, g1 = 0.f;
     int cx0 = -1;
+    T zero;
+    from_f32(zero, 0.f);
     for (int s = 0; s < npts; ++s) {
       float val = 0.f;
       if (l >= 0) {
-        const float q[3] = {s_q[s][0], s_q[s][1], s_q[s][2]};
-        float pd[3];
-        displaced(q, d, pd);
-        const Axis3 ax = axis_border(pd[0], R);
+        const AxEntry e = axs[s];
         bool reload = false;
         if (s_new[s]) {
+          const float q[3] = {s_q[s][0], s_q[s][1], s_q[s][2]};
+          float pd[3];
+          displaced(q, d, pd);
           const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
           const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
           const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
@@ -230,18 +274,19 @@ __global__ void __launch_bounds__(kGridThreads) gather_grid_kernel(const GridGat
           }
           reload = true;
         }
-        if (reload || ax.i0 != cx0) {
+        if (reload || e.i0 != cx0) {
           auto row = [&](int xv) {
             float r = to_f32(vol[base[0] + static_cast<uint32_t>(xv) * C]) * wyz[0];
 #pragma unroll
             for (int k = 1; k < 4; ++k) r = fmaf(to_f32(vol[base[k] + static_cast<uint32_t>(xv) * C]), wyz[k], r);
             return r;
           };
-          g0 = (!reload && ax.i0 == cx0 + 1) ? g1 : row(ax.i0);
-          g1 = (ax.i1 != ax.i0) ? row(ax.i1) : g0;
-          cx0 = ax.i0;
+          const int i1 = min(e.i0 + 1, R - 1);
+          g0 = (!reload && e.i0 == cx0 + 1) ? g1 : row(e.i0);
+          g1 = (i1 != e.i0) ? row(i1) : g0;
+          cx0 = e.i0;
         }
-        val = fmaf(g1, ax.w1, g0 * ax.w0);
+        val = fmaf(g1 - g0, e.w1, g0);
       } else if (lane >= nscal && lane < nscal + 3) {
         val = s_q[s][lane - nscal];
       }
@@ -249,11 +294,7 @@ __global__ void __launch_bounds__(kGridThreads) gather_grid_kernel(const GridGat
       T o;
       from_f32(o, val);
       if (lane < ntail) row_out[lane] = o;
-      if (lane + 32 < ntail) {                          // columns beyond nscal+3 are padding (nscal+3 <= 32)
-        T z;
-        from_f32(z, 0.f);
-        row_out[lane + 32] = z;
-      }
+      if (lane + 32 < ntail) row_out[lane + 32] = zero;   // columns beyond nscal+3 are padding (nscal+3 <= 32)
     }
   }
 }
@@ -276,7 +317,7 @@ int gather_grid_walk(const ListCtx* ctx, int image, int res, double bb_min, doub
   p.S = ctx->map_size;
   p.Cm = ctx->map_channels;
   p.nlev = ctx->n_levels;
-  int n3d = 0, tail0 = lay.xyz_off;
+  int tail0 = lay.xyz_off;
   for (int l = 0; l < ctx->n_levels; ++l) {
     const size_t vox = static_cast<size_t>(ctx->vol_res[l]) * ctx->vol_res[l] * ctx->vol_res[l] * ctx->vol_ch[l];
     if (vox >= (1ull << 32)) return LIST_ENOSYS;      // 32-bit element offsets inside a volume
@@ -284,8 +325,7 @@ int gather_grid_walk(const ListCtx* ctx, int image, int res, double bb_min, doub
     p.R[l] = ctx->vol_res[l];
     p.C[l] = ctx->vol_ch[l];
     p.voff[l] = lay.vol_off[l];
-    if (ctx->vol_ch[l] % 8 == 0) n3d += LIST_NUM_DISP * (ctx->vol_ch[l] / 8);
-    else tail0 = lay.vol_off[l] < tail0 ? lay.vol_off[l] : tail0;
+    if (ctx->vol_ch[l] % 8 != 0) tail0 = lay.vol_off[l] < tail0 ? lay.vol_off[l] : tail0;
   }
   p.map_off = lay.map_off;
   p.xyz_off = lay.xyz_off;
@@ -294,14 +334,65 @@ int gather_grid_walk(const ListCtx* ctx, int image, int res, double bb_min, doub
   p.res = res;
   p.bb_min = bb_min;
   p.bb_max = bb_max;
-  p.n2d = ctx->map_channels / 8;
-  p.n3d = n3d;
-  if (p.n2d + p.n3d > kGridThreads - 32) return LIST_ENOSYS;
   if (lay.xyz_off + 3 - tail0 > 32 || lay.k_pad - tail0 > 64) return LIST_ENOSYS;
+
+  // ---- roles ----
+  int nr = 0;
+  for (int first = 0; first < ctx->map_channels / 8; first += kRoleThreads) {     // 2-D vectors
+    if (nr >= kMaxRoles) return LIST_ENOSYS;
+    GridRole& r = p.roles[nr++];
+    r.kind = 0;
+    r.first = first;
+    r.count = (ctx->map_channels / 8 - first) < kRoleThreads ? (ctx->map_channels / 8 - first) : kRoleThreads;
+  }
+  {                                                   // 3-D vector levels, layout order, packed greedily
+    int item0 = 0;
+    GridRole cur{};
+    cur.kind = 1;
+    cur.first = 0;
+    for (int l = ctx->n_levels - 1; l >= 0; --l) {
+      if (ctx->vol_ch[l] % 8) continue;
+      int cnt = LIST_NUM_DISP * (ctx->vol_ch[l] / 8);
+      int done = 0;
+      while (done < cnt) {
+        const int room = kRoleThreads - cur.count;
+        const bool level_fits = (cnt - done) <= room && cur.nlev < kRoleLevels;
+        if (room == 0 || (!level_fits && cur.count > 0)) {            // close the current role
+          if (nr >= kMaxRoles) return LIST_ENOSYS;
+          p.roles[nr++] = cur;
+          cur = GridRole{};
+          cur.kind = 1;
+          cur.first = item0;
+          continue;
+        }
+        const int take = (cnt - done) < room ? (cnt - done) : room;
+        if (cur.nlev == 0 || cur.lev[cur.nlev - 1] != l) cur.lev[cur.nlev++] = l;
+        cur.count += take;
+        done += take;
+        item0 += take;
+      }
+    }
+    if (cur.count > 0) {
+      if (nr >= kMaxRoles) return LIST_ENOSYS;
+      p.roles[nr++] = cur;
+    }
+  }
+  {                                                   // scalar tail
+    if (nr >= kMaxRoles) return LIST_ENOSYS;
+    GridRole& r = p.roles[nr++];
+    r.kind = 2;
+    r.count = 32;
+    for (int l = 0; l < ctx->n_levels; ++l)
+      if (ctx->vol_ch[l] % 8) {
+        if (r.nlev >= kRoleLevels) return LIST_ENOSYS;
+        r.lev[r.nlev++] = l;
+      }
+  }
+  p.nroles = nr;
   if (count == 0) return LIST_OK;
-  const unsigned blocks = static_cast<unsigned>((count + kPz - 1) / kPz);
-  if (ctx->dtype == LIST_F32) gather_grid_kernel<float><<<blocks, kGridThreads, 0, st>>>(p);
-  else gather_grid_kernel<__nv_bfloat16><<<blocks, kGridThreads, 0, st>>>(p);
+  dim3 grid(static_cast<unsigned>((count + kPz - 1) / kPz), nr);
+  if (ctx->dtype == LIST_F32) gather_grid_kernel<float><<<grid, kRoleThreads, 0, st>>>(p);
+  else gather_grid_kernel<__nv_bfloat16><<<grid, kRoleThreads, 0, st>>>(p);
   LIST_LAUNCH_CHECK("gather_grid_kernel");
   return LIST_OK;
 }
