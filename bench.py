@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-chunks", type=int, default=2, help="65536-point chunks timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fused", action="store_true", help="bf16: chunked gather + MLP kernels instead of the fused kernel")
     return ap.parse_args()
 
 
@@ -159,6 +160,9 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if a.no_fused:
+        os.environ["LIST_B200_NO_FUSED"] = "1"
+    fused = a.dtype == "bf16" and os.environ.get("LIST_B200_NO_FUSED", "0") != "1"
 
     import torch
     import torch.distributed as dist
@@ -218,8 +222,33 @@ def main():
     checksum = float(full.double().sum().item())
 
     # ---- per-kernel timing for the roofline (same stream, CUDA events, after the timed region) ----
-    t_gather = t_mlp = 0.0
+    pk = peaks()
+    es = 2 if a.dtype == "bf16" else 4
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath))
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    roof_fused = None
+    if fused:
+        # the step IS one kernel launch (sdf_fused_kernel): time it alone
+        tf = []
+        for rep in range(3):
+            ev[0].record()
+            hotpath.grid_sdf(ctx, kw, res, begin, count, SDF_SCALE, chunk, out=local_out, workspace=ws)
+            ev[1].record()
+            torch.cuda.synchronize()
+            tf.append(ev[0].elapsed_time(ev[1]))
+        t_fused = sorted(tf)[1]
+        fl = FLOP_PER_QUERY * count / (t_fused * 1e-3) / 1e12
+        roof_fused = {"kernel": "sdf_fused_kernel", "bound": "tensor", "achieved": fl, "peak": pk["tensor"],
+                      "unit": "TFLOP/s", "frac": fl / pk["tensor"], "traffic": traffic.get("fused"),
+                      "ms_per_step": t_fused, "launches_per_step": 1, "peak_source": pk["src"],
+                      "note": "gather fused into the MLP kernel: feature rows never reach HBM, compulsory HBM bytes "
+                              "are 4 B/query of SDF + one read of the per-image tensors; reported against the "
+                              "tensor-core roofline only (SURVEY.md 8d)"}
+        os.environ["LIST_B200_NO_FUSED"] = "1"            # the unfused pair below, for comparison
+    t_gather = t_mlp = 0.0
     for rep in range(2):                                   # rep 0 warms the allocator
         tg = tm = 0.0
         for n0 in range(0, count, chunk):
@@ -234,25 +263,25 @@ def main():
             tm += ev[1].elapsed_time(ev[2])
             del X
         t_gather, t_mlp = tg, tm
-    pk = peaks()
-    es = 2 if a.dtype == "bf16" else 4
+    if fused:
+        os.environ.pop("LIST_B200_NO_FUSED", None)
     mlp_tflops = FLOP_PER_QUERY * count / (t_mlp * 1e-3) / 1e12
     feat_bytes = sum(t.numel() * t.element_size() for t in [ctx.maps_cl, *ctx.vols_cl])
     gather_bytes = count * lay.k_out * es + feat_bytes               # SURVEY.md §8d (q is generated in-kernel)
     gather_gbs = gather_bytes / (t_gather * 1e-3) / 1e9
-    traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath))
     roof_mlp = {"kernel": "mlp_tc_kernel" if a.dtype == "bf16" else "sgemm_kernel", "bound": "tensor",
                 "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
                 "traffic": traffic.get("mlp"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
                 "peak_source": pk["src"]}
     generic = os.environ.get("LIST_B200_GRID_GENERIC", "0") == "1"
-    roof_gather = {"kernel": "gather_fwd_kernel" if generic else "gather_grid_kernel", "bound": "hbm", "achieved": gather_gbs, "peak": pk["hbm"],
+    roof_gather = {"kernel": "gather_fwd_kernel" if generic else "gather_grid_kernel", "bound": "hbm",
+                   "achieved": gather_gbs, "peak": pk["hbm"],
                    "unit": "GB/s", "frac": gather_gbs / pk["hbm"], "traffic": traffic.get("gather"),
                    "ms_per_step": t_gather, "launches_per_step": n_chunks, "peak_source": pk["src"]}
-    dominant, other = (roof_mlp, roof_gather) if t_mlp >= t_gather else (roof_gather, roof_mlp)
+    if fused:
+        dominant, other = roof_fused, {"unfused_pair_for_comparison": [roof_gather, roof_mlp]}
+    else:
+        dominant, other = (roof_mlp, roof_gather) if t_mlp >= t_gather else (roof_gather, roof_mlp)
 
     # ---- end to end through the C ABI with HOST buffers (H2D + prep + grid + D2H inside the timed region) ----
     e2e = None
@@ -293,11 +322,12 @@ def main():
             "config": {"workload": f"cfg-4: LIST inference, 1 image (224x224 synthetic features), {res}^3 dense SDF grid "
                                    f"sharded by contiguous point ranges over {world} GPU(s) + one NCCL all_gather",
                        "grid_res": res, "queries_per_step": total, "chunk_rows": chunk, "sdf_scale": SDF_SCALE,
-                       "trans_mat": "camera-like", "mlp_variant": os.environ.get("LIST_B200_MLP_VARIANT", "2"),
-                       "l2": "no flush: every step streams 2 x rows x 7296 B of feature rows (>> 126 MB L2) plus "
-                             "132 MB of per-image tensors",
+                       "trans_mat": "camera-like", "kernel_path": "fused gather->MLP (sdf_fused_kernel)" if fused else
+                       "chunked gather + MLP kernels",
+                       "l2": "no flush: a step touches 16.8 M distinct queries over 132 MB of per-image tensors + 3.9 MB of "
+                             "weights re-streamed per 256-row tile; nothing is reused across steps but those",
                        "parallelism": f"grid-shard x{world}"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * n_chunks * 2,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * (1 if fused else n_chunks * 2),
             "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
             "checksum": checksum,
         }), flush=True)

@@ -42,6 +42,8 @@ int gather_bwd(const ListCtx* ctx, const float* q, int q_is_raw, int B, int64_t 
                const ListGrads* g, cudaStream_t st);
 int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
                float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
+int sdf_grid_fused(const ListCtx* ctx, const ListWeights* w, int image, int res, double bb_min, double bb_max,
+                   int64_t begin, int64_t count, float* sdf, float out_div, cudaStream_t st);
 
 static size_t elem_size(int dtype) { return dtype == LIST_BF16 ? 2 : 4; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -316,12 +318,25 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
                  (long long)begin, (long long)count);
   if (count == 0) return LIST_OK;
   LIST_CHECK_ARG(sdf != nullptr && sdf_scale != 0.f && chunk_rows >= 1, "list_sdf_grid: sdf NULL, sdf_scale 0 or chunk_rows < 1");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // bf16: ONE fused gather->MLP launch per image (sdf_fused.cu), no feature rows in HBM, no workspace.
+  // LIST_B200_NO_FUSED=1 (A/B aid) or an uncovered configuration -> chunked gather + MLP kernels.
+  const char* nf = getenv("LIST_B200_NO_FUSED");
+  bool fused = ctx->dtype == LIST_BF16 && !(nf && nf[0] == '1');
+  int b0 = 0;
+  if (fused) {
+    for (; b0 < ctx->B; ++b0) {
+      rc = sdf_grid_fused(ctx, w, b0, res, bb_min, bb_max, begin, count, sdf + static_cast<int64_t>(b0) * count, sdf_scale, st);
+      if (rc == LIST_ENOSYS && b0 == 0) { fused = false; break; }
+      if (rc) return rc;
+    }
+    if (fused) return LIST_OK;
+  }
   const size_t need = list_sdf_workspace_bytes(ctx, w, chunk_rows);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("list_sdf_grid: workspace %zu B < required %zu B", workspace_bytes, need);
     return LIST_ENOMEM;
   }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
   void* X = workspace;
   void* mlp_ws = static_cast<char*>(workspace) + xb;
