@@ -162,7 +162,8 @@ def main():
         return run_reference(a)
     if a.no_fused:
         os.environ["LIST_B200_NO_FUSED"] = "1"
-    fused = a.dtype == "bf16" and os.environ.get("LIST_B200_NO_FUSED", "0") != "1"
+    fused = (a.dtype == "bf16" and os.environ.get("LIST_B200_NO_FUSED", "0") != "1"
+             and os.environ.get("LIST_B200_FUSED", "0") == "1")
 
     import torch
     import torch.distributed as dist

@@ -91,6 +91,13 @@ static int grid_gather(const ListCtx* ctx, int image, int res, double bb_min, do
   return gather_grid_fwd(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, st);
 }
 
+// The fused kernel is used when it is the faster path (LIST_B200_FUSED=1/0 overrides).
+static bool fused_default() {
+  const char* e = getenv("LIST_B200_FUSED");
+  if (e) return e[0] == '1';
+  return false;
+}
+
 static int mlp_variant() {
   // LIST_B200_MLP_VARIANT=1 selects the single-CTA tcgen05 kernel (bring-up aid); default CTA pair.
   const char* e = getenv("LIST_B200_MLP_VARIANT");
@@ -322,7 +329,7 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
   // bf16: ONE fused gather->MLP launch per image (sdf_fused.cu), no feature rows in HBM, no workspace.
   // LIST_B200_NO_FUSED=1 (A/B aid) or an uncovered configuration -> chunked gather + MLP kernels.
   const char* nf = getenv("LIST_B200_NO_FUSED");
-  bool fused = ctx->dtype == LIST_BF16 && !(nf && nf[0] == '1');
+  bool fused = ctx->dtype == LIST_BF16 && !(nf && nf[0] == '1') && fused_default();
   int b0 = 0;
   if (fused) {
     for (; b0 < ctx->B; ++b0) {

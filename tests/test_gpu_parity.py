@@ -191,6 +191,7 @@ def test_fused_grid_kernel_equals_chunked_gather_plus_mlp(monkeypatch):
     ctx, kw = ctx_and_weights(g, "bf16")
     for res, begin, count in ((24, 0, 24 ** 3), (40, 12345, 20000), (16, 7, 300), (9, 0, 729)):
         monkeypatch.delenv("LIST_B200_NO_FUSED", raising=False)
+        monkeypatch.setenv("LIST_B200_FUSED", "1")
         fused = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0)
         monkeypatch.setenv("LIST_B200_NO_FUSED", "1")
         chunked = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=4096)
