@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblist_b200.so")
+LIB_PATH = os.environ.get("LIST_B200_LIB") or os.path.join(HERE, "liblist_b200.so")   # override: A/B builds only
 
 ABI_VERSION = 1
 MAX_LEVELS = 8

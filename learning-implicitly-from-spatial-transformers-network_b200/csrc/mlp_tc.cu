@@ -209,7 +209,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       const long long row = tile * rows_per_tile + rank * BM + quarter * 32 + lane;
       // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
-      mbar_wait(dfull_bar, dphase); dphase ^= 1;
+      mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < N0 / 32; ++j) {
@@ -233,7 +233,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       if (CG == 2) mbar_arrive_cluster(hready_remote);
       else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
       // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) ----
-      mbar_wait(dfull_bar, dphase); dphase ^= 1;
+      mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
 #pragma unroll 1
       for (int j = 0; j < N1 / 32; ++j) {
@@ -257,7 +257,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       if (CG == 2) mbar_arrive_cluster(hready_remote);
       else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
       // ---- after fc_2: sdf = (relu(acc + b2) · w3 + b3) / out_div ----
-      mbar_wait(dfull_bar, dphase); dphase ^= 1;
+      mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       float acc = 0.f;
 #pragma unroll 1
