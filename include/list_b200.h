@@ -169,6 +169,22 @@ LIST_API int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float*
                  int32_t B, int64_t N, float* sdf, float out_div, int64_t chunk_rows,
                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* Hoisted fc_0 for dense grids in bf16 mode (csrc/hoist.cu).  fc_0 (reference modules.py:197,276) and the
+ * samplers in front of it (modules.py:48-52, 264-265) are linear, so the maps and the coarse voxel levels
+ * (R <= 16) are projected through their column blocks of W0 once per image and sampled per query as ONE
+ * 512-wide addend block; the feature row shrinks from 3648 to 1344 columns and W0 to
+ * W0h = [I_512 | remaining columns].  list_sdf_grid does all of this internally; the three calls below expose
+ * the stages for tests and per-kernel timing.
+ *   list_hoist_bytes            size of the caller-owned buffer holding W0h + projected tensors (0: not hoistable)
+ *   list_hoist_prepare          projects every image of ctx and builds W0h; *w_hoisted = *w with w0 / k_pad replaced
+ *   list_hoist_gather_grid_fwd  hoisted rows X[count][ldx >= k_h] for grid points [begin, begin+count) of `image` */
+LIST_API size_t list_hoist_bytes(const ListCtx* ctx, const ListWeights* w);
+LIST_API int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes,
+                       ListWeights* w_hoisted, void* stream);
+LIST_API int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image,
+                               int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count,
+                               void* X, int64_t ldx, void* stream);
+
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
  * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */
 LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min,

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "common.cuh"
+#include "hoist.cuh"
 
 namespace list {
 
@@ -99,9 +100,92 @@ static bool fused_default() {
 }
 
 static int mlp_variant() {
-  // LIST_B200_MLP_VARIANT=1 selects the single-CTA tcgen05 kernel (bring-up aid); default CTA pair.
+  // LIST_B200_MLP_VARIANT=1 selects the single-CTA tcgen05 kernel (bring-up aid), 3 the CTA pair with a
+  // 3-stage operand ring; default CTA pair with 4 stages.
   const char* e = getenv("LIST_B200_MLP_VARIANT");
-  return (e && e[0] == '1') ? 1 : 2;
+  if (e && e[0] == '1') return 1;
+  if (e && e[0] == '3') return 3;
+  return 2;
+}
+
+// ---- two-stream chunk pipeline ------------------------------------------------------------
+// The gather is issue/HBM-write bound and the tensor-core MLP is tensor-pipe bound, so the gather of
+// chunk i+1 runs CONCURRENTLY with the MLP of chunk i: the gather is enqueued on a low-priority
+// auxiliary stream, the MLP on a high-priority one, X is double buffered and events order them.  Both
+// auxiliary streams are forked from / joined to the caller's stream with events, so the caller still
+// sees plain stream semantics (everything enqueued, nothing synchronised, graph-capturable).
+// The streams and events are created lazily once per (host thread, device): thread_local keeps the
+// entry points re-entrant (nn.DataParallel replicas call from parallel host threads).
+struct Pipe {
+  int device = -1;
+  cudaStream_t lo = nullptr, hi = nullptr;
+  cudaEvent_t fork = nullptr, ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+};
+static constexpr int kMaxPipeDevices = 16;
+static thread_local Pipe g_pipes[kMaxPipeDevices];
+
+static int get_pipe(Pipe** out) {
+  int dev = 0;
+  LIST_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxPipeDevices) { set_error("device %d outside the pipeline table", dev); return LIST_ENOSYS; }
+  Pipe& p = g_pipes[dev];
+  if (p.device != dev) {
+    int least = 0, greatest = 0;
+    LIST_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    LIST_CUDA(cudaStreamCreateWithPriority(&p.lo, cudaStreamNonBlocking, least));
+    LIST_CUDA(cudaStreamCreateWithPriority(&p.hi, cudaStreamNonBlocking, greatest));
+    LIST_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+      LIST_CUDA(cudaEventCreateWithFlags(&p.ready[i], cudaEventDisableTiming));
+      LIST_CUDA(cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming));
+    }
+    p.device = dev;
+  }
+  *out = &p;
+  return LIST_OK;
+}
+
+// Hoisted fc_0 (hoist.cu) is the default dense-grid path in bf16 mode; LIST_B200_HOIST=0 selects the
+// plain full-row gather + MLP (A/B aid).
+static bool hoist_enabled() {
+  const char* e = getenv("LIST_B200_HOIST");
+  return !(e && e[0] == '0');
+}
+
+static bool overlap_enabled() {
+  const char* e = getenv("LIST_B200_OVERLAP");
+  return !(e && e[0] == '0');
+}
+
+// Runs `n_items` (gather_i -> mlp_i) pairs.  gather(i, X, stream) fills X; mlp(i, X, stream) consumes it.
+// xbuf[0], xbuf[1]: two feature-row buffers; with overlap == false only xbuf[0] is used, serially on `st`.
+template <typename G, typename M>
+static int run_chunks(int64_t n_items, void* const xbuf[2], bool overlap, cudaStream_t st, G gather, M mlp) {
+  int rc;
+  if (!overlap || n_items < 2) {
+    for (int64_t i = 0; i < n_items; ++i) {
+      if ((rc = gather(i, xbuf[0], st))) return rc;
+      if ((rc = mlp(i, xbuf[0], st))) return rc;
+    }
+    return LIST_OK;
+  }
+  Pipe* p = nullptr;
+  if ((rc = get_pipe(&p))) return rc;
+  LIST_CUDA(cudaEventRecord(p->fork, st));
+  LIST_CUDA(cudaStreamWaitEvent(p->lo, p->fork, 0));
+  LIST_CUDA(cudaStreamWaitEvent(p->hi, p->fork, 0));
+  for (int64_t i = 0; i < n_items; ++i) {
+    const int b = static_cast<int>(i & 1);
+    if (i >= 2) LIST_CUDA(cudaStreamWaitEvent(p->lo, p->freed[b], 0));   // MLP of item i-2 has read xbuf[b]
+    if ((rc = gather(i, xbuf[b], p->lo))) return rc;
+    LIST_CUDA(cudaEventRecord(p->ready[b], p->lo));
+    LIST_CUDA(cudaStreamWaitEvent(p->hi, p->ready[b], 0));
+    if ((rc = mlp(i, xbuf[b], p->hi))) return rc;
+    LIST_CUDA(cudaEventRecord(p->freed[b], p->hi));
+  }
+  // join: every gather is ordered before an MLP on `hi`; its last event joins the caller's stream
+  LIST_CUDA(cudaStreamWaitEvent(st, p->freed[(n_items - 1) & 1], 0));
+  return LIST_OK;
 }
 
 }  // namespace list
@@ -265,7 +349,62 @@ size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_
   ListLayout lay;
   if (list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr)) return 0;
   const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
-  return xb + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+  // bf16: two feature-row buffers (gather of chunk i+1 overlaps the MLP of chunk i) + the hoisted-fc_0 tensors of
+  // list_sdf_grid (projected maps / coarse volumes, W0h); fp32: one buffer + MLP activations
+  size_t extra = 0;
+  hoist::Plan pl;
+  if (ctx->dtype == LIST_BF16 && hoist::make_plan(ctx, w, &pl) == LIST_OK) extra = align_up(pl.total, 256);
+  return (ctx->dtype == LIST_BF16 ? 2 * xb : xb) + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256) + extra;
+}
+
+size_t list_hoist_bytes(const ListCtx* ctx, const ListWeights* w) {
+  if (!ctx || !w) return 0;
+  hoist::Plan pl;
+  if (check_ctx(ctx) || check_weights(w, -1) || hoist::make_plan(ctx, w, &pl) != LIST_OK) return 0;
+  return pl.total;
+}
+
+int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, ListWeights* w_hoisted,
+                       void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if ((rc = check_weights(w, -1))) return rc;
+  hoist::Plan pl;
+  if (hoist::make_plan(ctx, w, &pl) != LIST_OK) {
+    set_error("list_hoist_prepare: this configuration has no hoisted path (bf16, fc_0 width 512, coarse levels with C %% 64 == 0)");
+    return LIST_ENOSYS;
+  }
+  if (!hoist_buf || hoist_bytes < pl.total || (reinterpret_cast<uintptr_t>(hoist_buf) & 255)) {
+    set_error("list_hoist_prepare: hoist_buf NULL, not 256B aligned or %zu B < required %zu B", hoist_bytes, pl.total);
+    return LIST_ENOMEM;
+  }
+  if ((rc = hoist::prepare(ctx, w, pl, hoist_buf, static_cast<cudaStream_t>(stream)))) return rc;
+  if (w_hoisted) {
+    *w_hoisted = *w;
+    w_hoisted->w0 = static_cast<char*>(hoist_buf) + pl.off_w0h;
+    w_hoisted->k_pad = pl.k_h;
+  }
+  return LIST_OK;
+}
+
+int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
+                               double bb_min, double bb_max, int64_t begin, int64_t count, void* X, int64_t ldx, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if ((rc = check_weights(w, -1))) return rc;
+  hoist::Plan pl;
+  if (hoist::make_plan(ctx, w, &pl) != LIST_OK || hoist::check_gather(ctx, pl, res) != LIST_OK) {
+    set_error("list_hoist_gather_grid_fwd: configuration / res %d not covered by the hoisted gather", res);
+    return LIST_ENOSYS;
+  }
+  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_hoist_gather_grid_fwd: image %d outside [0,%d)", image, ctx->B);
+  LIST_CHECK_ARG(res >= 1 && res <= 2048, "list_hoist_gather_grid_fwd: res %d out of range", res);
+  const int64_t total = static_cast<int64_t>(res) * res * res;
+  LIST_CHECK_ARG(begin >= 0 && count >= 0 && begin + count <= total, "list_hoist_gather_grid_fwd: [%lld,+%lld) outside res^3",
+                 (long long)begin, (long long)count);
+  LIST_CHECK_ARG(hoist_buf && X && ldx >= pl.k_h && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
+                 "list_hoist_gather_grid_fwd: hoist_buf/X NULL, X unaligned or ldx %lld < %d", (long long)ldx, pl.k_h);
+  return hoist::gather(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, X, ldx, static_cast<cudaStream_t>(stream));
 }
 
 int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw, int32_t B, int64_t N, float* sdf,
@@ -287,11 +426,14 @@ int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32
   }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
-  void* X = workspace;
-  void* mlp_ws = static_cast<char*>(workspace) + xb;
+  const bool two = ctx->dtype == LIST_BF16;
+  void* const xbuf[2] = {workspace, two ? static_cast<char*>(workspace) + xb : workspace};
+  const size_t mlp_off = two ? 2 * xb : xb;
+  void* mlp_ws = static_cast<char*>(workspace) + mlp_off;
   // per image, chunks of the point range; one image at a time keeps the ctx indexing trivial
-  ListCtx one = *ctx;
-  for (int b = 0; b < B; ++b) {
+  const int64_t per_image = (N + chunk_rows - 1) / chunk_rows;
+  auto one_image = [&](int b) {
+    ListCtx one = *ctx;
     one.B = 1;
     one.maps = static_cast<const char*>(ctx->maps) + static_cast<size_t>(b) * ctx->map_size * ctx->map_size * ctx->map_channels * elem_size(ctx->dtype);
     for (int l = 0; l < ctx->n_levels; ++l) {
@@ -299,15 +441,27 @@ int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32
       one.vols[l] = static_cast<const char*>(ctx->vols[l]) + static_cast<size_t>(b) * vox * elem_size(ctx->dtype);
     }
     one.trans_mat = ctx->trans_mat + b * 12;
-    for (int64_t n0 = 0; n0 < N; n0 += chunk_rows) {
-      const int64_t n = (N - n0 < chunk_rows) ? (N - n0) : chunk_rows;
-      if ((rc = gather_fwd(&one, q + (static_cast<int64_t>(b) * N + n0) * 3, q_is_raw, X, lay.k_pad, 1, n, st))) return rc;
-      if ((rc = list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * N + n0, out_div, mlp_ws,
-                             workspace_bytes - xb, stream)))
-        return rc;
-    }
-  }
-  return LIST_OK;
+    return one;
+  };
+  auto span = [&](int64_t i, int& b, int64_t& n0, int64_t& n) {
+    b = static_cast<int>(i / per_image);
+    n0 = (i % per_image) * chunk_rows;
+    n = (N - n0 < chunk_rows) ? (N - n0) : chunk_rows;
+  };
+  return run_chunks(
+      per_image * B, xbuf, two && overlap_enabled(), st,
+      [&](int64_t i, void* X, cudaStream_t s) {
+        int b; int64_t n0, n;
+        span(i, b, n0, n);
+        const ListCtx one = one_image(b);
+        return gather_fwd(&one, q + (static_cast<int64_t>(b) * N + n0) * 3, q_is_raw, X, lay.k_pad, 1, n, s);
+      },
+      [&](int64_t i, void* X, cudaStream_t s) {
+        int b; int64_t n0, n;
+        span(i, b, n0, n);
+        return list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * N + n0, out_div, mlp_ws,
+                            workspace_bytes - mlp_off, s);
+      });
 }
 
 int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
@@ -345,18 +499,51 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
     return LIST_ENOMEM;
   }
   const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
-  void* X = workspace;
-  void* mlp_ws = static_cast<char*>(workspace) + xb;
-  for (int b = 0; b < ctx->B; ++b) {
-    for (int64_t n0 = 0; n0 < count; n0 += chunk_rows) {
-      const int64_t n = (count - n0 < chunk_rows) ? (count - n0) : chunk_rows;
-      if ((rc = grid_gather(ctx, b, res, bb_min, bb_max, begin + n0, n, X, lay.k_pad, st))) return rc;
-      if ((rc = list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, mlp_ws,
-                             workspace_bytes - xb, stream)))
-        return rc;
-    }
+  const bool two = ctx->dtype == LIST_BF16;
+  void* const xbuf[2] = {workspace, two ? static_cast<char*>(workspace) + xb : workspace};
+  const size_t mlp_off = two ? 2 * xb : xb;
+  void* mlp_ws = static_cast<char*>(workspace) + mlp_off;
+  const int64_t per_image = (count + chunk_rows - 1) / chunk_rows;
+  auto span = [&](int64_t i, int& b, int64_t& n0, int64_t& n) {
+    b = static_cast<int>(i / per_image);
+    n0 = (i % per_image) * chunk_rows;
+    n = (count - n0 < chunk_rows) ? (count - n0) : chunk_rows;
+  };
+  // bf16: hoisted fc_0 (hoist.cu) -- project maps / coarse levels through their W0 blocks once per call, then the
+  // per-chunk gather writes the 1344-column hoisted row and the MLP runs on W0h.
+  hoist::Plan pl;
+  if (two && hoist_enabled() && hoist::make_plan(ctx, w, &pl) == LIST_OK && hoist::check_gather(ctx, pl, res) == LIST_OK) {
+    void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+    if ((rc = hoist::prepare(ctx, w, pl, hbuf, st))) return rc;
+    ListWeights wh = *w;
+    wh.w0 = static_cast<char*>(hbuf) + pl.off_w0h;
+    wh.k_pad = pl.k_h;
+    return run_chunks(
+        per_image * ctx->B, xbuf, overlap_enabled(), st,
+        [&](int64_t i, void* X, cudaStream_t s) {
+          int b; int64_t n0, n;
+          span(i, b, n0, n);
+          return hoist::gather(ctx, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, s);
+        },
+        [&](int64_t i, void* X, cudaStream_t s) {
+          int b; int64_t n0, n;
+          span(i, b, n0, n);
+          return list_mlp_fwd(&wh, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, nullptr, 0, s);
+        });
   }
-  return LIST_OK;
+  return run_chunks(
+      per_image * ctx->B, xbuf, two && overlap_enabled(), st,
+      [&](int64_t i, void* X, cudaStream_t s) {
+        int b; int64_t n0, n;
+        span(i, b, n0, n);
+        return grid_gather(ctx, b, res, bb_min, bb_max, begin + n0, n, X, lay.k_pad, s);
+      },
+      [&](int64_t i, void* X, cudaStream_t s) {
+        int b; int64_t n0, n;
+        span(i, b, n0, n);
+        return list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, mlp_ws,
+                            workspace_bytes - mlp_off, s);
+      });
 }
 
 // ---- host-buffer variant -----------------------------------------------------------------
@@ -379,6 +566,14 @@ static void plan_host(const int32_t* map_ch, const int32_t* map_in, int n_maps, 
   ListLayout lay;
   list_feature_layout(cm, n_levels, vol_ch, &lay, nullptr);
   size_t ws = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(dtype), 256);
+  if (dtype == LIST_BF16) {
+    ws *= 2;                                           // double-buffered feature rows (run_chunks)
+    // hoisted-fc_0 tensors (hoist.cu): W0h + projected maps + 7 projected copies of every level with R <= 16
+    size_t h = align_up(static_cast<size_t>(512) * lay.k_pad * 2, 256) + align_up(static_cast<size_t>(B) * S * S * 512 * 2, 256);
+    for (int l = 0; l < n_levels; ++l)
+      if (vol_res[l] <= 16) h += align_up(static_cast<size_t>(7) * B * vol_res[l] * vol_res[l] * vol_res[l] * 512 * 2, 256);
+    ws += h + 256;
+  }
   if (dtype == LIST_F32) ws += align_up(static_cast<size_t>(chunk_rows) * (512 + 256 + 256) * 4, 256);
   p->ws = take(ws);
   p->total = off;

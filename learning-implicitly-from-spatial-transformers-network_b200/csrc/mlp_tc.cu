@@ -32,12 +32,12 @@ constexpr int SUB_BYTES = 128 * BK * 2; // one 128-row weight box, 16 KB
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
 
-template <int CG>
+template <int CG, int ST>
 struct Cfg {
   static constexpr int SUBS_L0 = (N0 / 128) / CG;     // weight boxes per CTA per fc_0 chunk
   static constexpr int SUBS_L12 = (N1 / 128) / CG;    // per fc_1 / fc_2 chunk
   static constexpr int STAGE_BYTES = A_BYTES + SUBS_L0 * SUB_BYTES;
-  static constexpr int STAGES = CG == 1 ? 2 : 4;
+  static constexpr int STAGES = ST;
   static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
   static constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;   // b0 b1 b2 w3
   static constexpr int BAR_OFF = RING_BYTES + PARAM_FLOATS * 4;
@@ -45,15 +45,16 @@ struct Cfg {
 };
 
 // ------------------------------------------------------------------ kernel
-template <int CG>
+template <int CG, int ST>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
               const float* __restrict__ b0, const float* __restrict__ b1, const float* __restrict__ b2,
               const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ sdf,
               long long rows, int nk0, float out_div, float* __restrict__ dbg1, float* __restrict__ dbg2,
-              float* __restrict__ dbg3) {
-  using C = Cfg<CG>;
+              float* __restrict__ dbg3, __nv_bfloat16* __restrict__ proj_out, int proj_groups, int proj_w_col_stride,
+              long long proj_out_group_stride) {
+  using C = Cfg<CG, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;               // SWIZZLE_128B tiles need 1024 B alignment
@@ -76,7 +77,13 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const int cluster_id = blockIdx.x / CG;
   const int num_clusters = gridDim.x / CG;
   const long long rows_per_tile = static_cast<long long>(BM) * CG;
-  const int num_tiles = static_cast<int>((rows + rows_per_tile - 1) / rows_per_tile);
+  // Projection mode (proj_out != nullptr, hoist.cu): only fc_0 runs, without bias/ReLU, and the raw
+  // 128 x 512 accumulator is written as bf16 rows.  The tile index then also enumerates `proj_groups`
+  // column blocks of W0 (block g starts at column g * proj_w_col_stride): every group multiplies the same
+  // X rows and writes its own [rows][512] output slab.
+  const bool proj = proj_out != nullptr;
+  const int tiles_per_group = static_cast<int>((rows + rows_per_tile - 1) / rows_per_tile);
+  const int num_tiles = proj ? tiles_per_group * proj_groups : tiles_per_group;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -116,7 +123,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     if (lane == 0) {
       uint32_t slot = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int row0 = static_cast<int>(tile * rows_per_tile + rank * BM);
+        const int group = tile / tiles_per_group;
+        const int row0 = static_cast<int>((tile - group * tiles_per_group) * rows_per_tile + rank * BM);
+        const int wcol0 = group * proj_w_col_stride;
         for (int kc = 0; kc < nk0; ++kc, ++slot) {                    // fc_0: X chunk + W0 chunk
           const int s = slot % C::STAGES;
           mbar_wait(empty_bar(s), ((slot / C::STAGES) & 1) ^ 1);
@@ -126,9 +135,10 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < C::SUBS_L0; ++j) {
             const int wrow = (CG == 1) ? j * 128 : j * 256 + static_cast<int>(rank) * 128;
-            tma_load_2d<CG>(&tmW0, fb, stage_b(s) + j * SUB_BYTES, kc * BK, wrow);
+            tma_load_2d<CG>(&tmW0, fb, stage_b(s) + j * SUB_BYTES, wcol0 + kc * BK, wrow);
           }
         }
+        if (proj) continue;
 #pragma unroll 1
         for (int layer = 1; layer <= 2; ++layer) {                    // fc_1 / fc_2: weights only
           const CUtensorMap* tm = (layer == 1) ? &tmW1 : &tmW2;
@@ -176,6 +186,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           umma_commit<CG>(empty_bar(s));
         }
         umma_commit<CG>(dfull_bar);
+        if (proj) continue;
         // ---- fc_1: D[256,512) = H1(TMEM [0,256)) · W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) · W2^T ----
 #pragma unroll 1
         for (int layer = 1; layer <= 2; ++layer) {
@@ -207,10 +218,34 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const float bias3 = __ldg(b3);
     uint32_t dphase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-      const long long row = tile * rows_per_tile + rank * BM + quarter * 32 + lane;
+      const int group = tile / tiles_per_group;
+      const long long row = (tile - group * tiles_per_group) * rows_per_tile + rank * BM + quarter * 32 + lane;
       // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
+      if (proj) {                                           // raw accumulator -> bf16 row of the group's slab
+        __nv_bfloat16* const orow = proj_out + group * proj_out_group_stride + row * N0;
+#pragma unroll 1
+        for (int j = 0; j < N0 / 32; ++j) {
+          uint32_t v[32];
+          tmem_ld32(tq + j * 32, v);
+          if (row < rows) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+              u.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+              u.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+              u.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+              *reinterpret_cast<uint4*>(orow + j * 32 + 8 * i) = u;
+            }
+          }
+        }
+        tc_fence_before();
+        if (CG == 2) mbar_arrive_cluster(hready_remote);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+        continue;
+      }
 #pragma unroll 1
       for (int j = 0; j < N0 / 32; ++j) {
         uint32_t v[32], u[16];
@@ -290,22 +325,32 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------ host side
-template <int CG>
+struct ProjArgs {                       // projection mode (see the kernel); all zero = the full MLP
+  __nv_bfloat16* out = nullptr;         // [groups][rows][512]
+  int groups = 1;
+  int w_col_stride = 0;                 // columns of W0 between consecutive groups
+  int k = 0;                            // K of the projection (columns of X and of each W0 block)
+};
+
+template <int CG, int ST>
 static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div,
-                  float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
-  using C = Cfg<CG>;
+                  float* dbg1, float* dbg2, float* dbg3, const ProjArgs& pa, cudaStream_t st) {
+  using C = Cfg<CG, ST>;
   CUtensorMap tmX, tmW0, tmW1, tmW2;
   int rc;
-  if ((rc = make_map_bf16(&tmX, X, w->k_pad, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx)))) return rc;
-  if ((rc = make_map_bf16(&tmW0, w->w0, w->k_pad, N0, w->k_pad))) return rc;
+  const bool proj = pa.out != nullptr;
+  const int k0 = proj ? pa.k : w->k_pad;
+  const uint64_t w0_cols = proj ? static_cast<uint64_t>(pa.w_col_stride) * (pa.groups - 1) + pa.k : w->k_pad;
+  if ((rc = make_map_bf16(&tmX, X, k0, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx)))) return rc;
+  if ((rc = make_map_bf16(&tmW0, w->w0, w0_cols, N0, w->k_pad))) return rc;
   if ((rc = make_map_bf16(&tmW1, w->w1, N0, N1, N0))) return rc;
   if ((rc = make_map_bf16(&tmW2, w->w2, N1, N2, N1))) return rc;
   int dev = 0, sms = 0;
   LIST_CUDA(cudaGetDevice(&dev));
   LIST_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  LIST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  LIST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
   const int64_t rows_per_tile = static_cast<int64_t>(BM) * CG;
-  const int64_t tiles = (rows + rows_per_tile - 1) / rows_per_tile;
+  const int64_t tiles = (rows + rows_per_tile - 1) / rows_per_tile * (proj ? pa.groups : 1);
   const int clusters = static_cast<int>(tiles < (sms / CG) ? tiles : (sms / CG));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CG);
@@ -319,9 +364,10 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  const int nk0 = w->k_pad / BK;
-  LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
-                               sdf, static_cast<long long>(rows), nk0, out_div, dbg1, dbg2, dbg3));
+  const int nk0 = k0 / BK;
+  LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG, ST>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
+                               sdf, static_cast<long long>(rows), nk0, out_div, dbg1, dbg2, dbg3, pa.out, pa.groups,
+                               pa.w_col_stride, static_cast<long long>(rows) * N0));
   return LIST_OK;
 }
 
@@ -337,8 +383,36 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
   LIST_CHECK_ARG(ldx % 8 == 0 && ldx >= w->k_pad, "mlp_tc: ldx %lld must be >= k_pad and a multiple of 8", (long long)ldx);
   LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "mlp_tc: X must be 16-byte aligned");
   LIST_CHECK_ARG(rows < (1LL << 31), "mlp_tc: rows %lld too large for one call", (long long)rows);
-  if (variant == 1) return tc::launch<1>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, st);
-  return tc::launch<2>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, st);
+  const tc::ProjArgs none;
+  if (variant == 1) return tc::launch<1, 2>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, st);
+  // variant 2 = CTA pair with a 4-stage operand ring (192 KB); variant 3 = the same with 3 stages (144 KB),
+  // which leaves shared memory for gather CTAs of the next chunk to co-reside on the SM (api.cu pipeline).
+  if (variant == 3) return tc::launch<2, 3>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, st);
+  return tc::launch<2, 4>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, st);
+}
+
+// Projection through fc_0 only (hoist.cu): out[g][r][0..512) = sum_k X[r][k] * W0[n][col0 + g*col_stride + k],
+// g < groups, bf16 in, fp32 accumulate on tcgen05, bf16 out, no bias / activation.  `w` supplies W0
+// (row pitch w->k_pad); X is [rows][ldx] bf16 with k <= ldx columns used.
+int mlp_tc_project(const ListWeights* w, int col0, int col_stride, int groups, int k, const void* X, int64_t ldx,
+                   int64_t rows, void* out, cudaStream_t st) {
+  if (rows == 0 || groups == 0) return LIST_OK;
+  LIST_CHECK_ARG(w->n0 == tc::N0, "mlp_tc_project: fc_0 width must be 512 (got %d)", w->n0);
+  LIST_CHECK_ARG(k > 0 && k % tc::BK == 0 && ldx >= k && ldx % 8 == 0, "mlp_tc_project: k %d must be a positive multiple of 64 and <= ldx %lld",
+                 k, (long long)ldx);
+  LIST_CHECK_ARG(col0 % 8 == 0 && col_stride % 8 == 0 && col0 + static_cast<int64_t>(col_stride) * (groups - 1) + k <= w->k_pad,
+                 "mlp_tc_project: W0 column block [%d + g*%d, +%d) outside k_pad %d or unaligned", col0, col_stride, k, w->k_pad);
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "mlp_tc_project: X/out must be 16-byte aligned");
+  LIST_CHECK_ARG(rows * groups < (1LL << 31), "mlp_tc_project: too many rows");
+  ListWeights wv = *w;                                    // view of W0 starting at column col0
+  wv.w0 = static_cast<const __nv_bfloat16*>(w->w0) + col0;
+  tc::ProjArgs pa;
+  pa.out = static_cast<__nv_bfloat16*>(out);
+  pa.groups = groups;
+  pa.w_col_stride = col_stride;
+  pa.k = k;
+  return tc::launch<2, 4>(&wv, X, ldx, rows, nullptr, 1.0f, nullptr, nullptr, nullptr, pa, st);
 }
 
 }  // namespace list

@@ -236,6 +236,47 @@ def gather_grid_features(ctx: HotPathContext, image: int, res: int, begin: int, 
     return X
 
 
+# ------------------------------------------------------------------------------ hoisted fc_0 (dense grids, bf16)
+class HoistedState:
+    """Output of list_hoist_prepare: the caller-owned buffer with W0h and the projected maps / coarse levels
+    (csrc/hoist.cu), plus the ListWeights view whose w0 is W0h.  Quacks like KernelWeights for `mlp`."""
+
+    def __init__(self, ctx: HotPathContext, weights: KernelWeights):
+        dev = _require_cuda(ctx.maps_cl, weights.w0)
+        lib = _C.lib()
+        self.ctx, self.base = ctx, weights
+        cs, ws = ctx.struct(), weights.struct()
+        need = lib.list_hoist_bytes(C.byref(cs), C.byref(ws))
+        if need == 0:
+            raise RuntimeError("list_hoist_bytes returned 0: this configuration has no hoisted path")
+        self.buf = torch.empty(need, device=dev, dtype=torch.uint8)
+        self._w = _C.ListWeights()
+        with torch.cuda.device(dev):
+            _C.check(lib.list_hoist_prepare(C.byref(cs), C.byref(ws), self.buf.data_ptr(), need, C.byref(self._w), _stream()),
+                     "list_hoist_prepare")
+        self.k_h = self._w.k_pad
+        self.dtype = weights.dtype
+        self.w0 = self.buf                      # device check in mlp()
+
+    def struct(self) -> _C.ListWeights:
+        return self._w
+
+    def w0h(self) -> torch.Tensor:
+        """W0h as a (512, k_h) bf16 tensor (a view of the buffer)."""
+        n0 = self.base.w0.shape[0]
+        return self.buf[: n0 * self.k_h * 2].view(torch.bfloat16).view(n0, self.k_h)
+
+    def gather_grid(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5):
+        dev = self.buf.device
+        X = torch.empty(count, self.k_h, device=dev, dtype=torch.bfloat16)
+        cs, ws = self.ctx.struct(), self.base.struct()
+        with torch.cuda.device(dev):
+            _C.check(_C.lib().list_hoist_gather_grid_fwd(C.byref(cs), C.byref(ws), self.buf.data_ptr(), image, res, bb_min,
+                                                         bb_max, begin, count, X.data_ptr(), self.k_h, _stream()),
+                     "list_hoist_gather_grid_fwd")
+        return X
+
+
 def mlp(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0, return_workspace: bool = False):
     """Row a-6 on feature rows X (rows, ldx)."""
     dev = _require_cuda(X, weights.w0)

@@ -171,7 +171,9 @@ def test_grid_kernel_vs_explicit_points_and_shards_compose(mode, res, monkeypatc
     whole = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=total)
     pts = hotpath.grid_points(res).unsqueeze(0).expand(2, -1, -1).contiguous()
     explicit = hotpath.query_sdf(ctx, kw, pts, out_div=10.0, chunk_rows=4096)
-    tol = 2e-6 if mode == "fp32" else 1e-3          # bf16: a re-associated feature may round to the other bf16 neighbour
+    # bf16: the dense-grid path hoists fc_0 through the samplers (csrc/hoist.cu), so it rounds to bf16 at different
+    # places than the per-point path; both stay far inside the 2e-2 bound (values here are SDF / 10)
+    tol = 2e-6 if mode == "fp32" else 2e-3
     assert (whole - explicit).abs().max().item() <= tol
     parts = []
     for begin, count in ((0, 1000), (1000, 5000), (6000, total - 6000)):
@@ -179,6 +181,7 @@ def test_grid_kernel_vs_explicit_points_and_shards_compose(mode, res, monkeypatc
     assert torch.equal(torch.cat(parts, dim=1), whole)
     monkeypatch.setenv("LIST_B200_GRID_GENERIC", "1")       # per-point kernel in grid mode ...
     monkeypatch.setenv("LIST_B200_NO_FUSED", "1")           # ... through the chunked gather + MLP path
+    monkeypatch.setenv("LIST_B200_HOIST", "0")              # ... on full (un-hoisted) feature rows
     generic = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=3000)
     assert torch.equal(generic, explicit)
 
@@ -189,6 +192,7 @@ def test_fused_grid_kernel_equals_chunked_gather_plus_mlp(monkeypatch):
     inp = synth.make_inputs(seed=13, B=2, N=8, size="small", trans="camera")
     g = inp.to(DEV)
     ctx, kw = ctx_and_weights(g, "bf16")
+    monkeypatch.setenv("LIST_B200_HOIST", "0")              # both sides on full (un-hoisted) feature rows
     for res, begin, count in ((24, 0, 24 ** 3), (40, 12345, 20000), (16, 7, 300), (9, 0, 729)):
         monkeypatch.delenv("LIST_B200_NO_FUSED", raising=False)
         monkeypatch.setenv("LIST_B200_FUSED", "1")
@@ -253,7 +257,7 @@ def test_full_size_256_grid_slab_properties():
         a = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0)
         pts = hotpath.grid_points(res, begin, count).unsqueeze(0)
         b = hotpath.query_sdf(ctx, kw, pts, out_div=10.0)
-        assert (a - b).abs().max().item() <= (2e-6 if mode == "fp32" else 1e-3)
+        assert (a - b).abs().max().item() <= (2e-6 if mode == "fp32" else 2e-3)
         out[mode] = a
     with torch.no_grad():
         ref = P.list_query(inp.maps, inp.vols, inp.trans_mat, hotpath.grid_points(res, begin, count).cpu().unsqueeze(0),
@@ -297,3 +301,43 @@ def test_backward_vs_reference_golden():
         assert abs(v.grad.double().sum().item() - float(z[f"dvol{i}_sum"])) <= 1e-3 * (abs(float(z[f"dvol{i}_sum"])) + 1)
     for i, m in enumerate(maps):
         assert rel(m.grad.flatten()[::13], z[f"dmap{i}_sub"]) <= tol
+
+
+# ------------------------------------------------------------------ hoisted fc_0 (dense grids, bf16)
+def test_hoisted_rows_addend_and_verbatim_columns():
+    """csrc/hoist.cu: the hoisted row is [addend(512) | the non-hoisted columns of the full row verbatim];
+    the addend equals W0[:, :hoist_cols] applied to the hoisted columns of the full (walker) row."""
+    inp = synth.make_inputs(seed=21, B=2, N=8, size="small", trans="camera")
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "bf16")
+    ctx32, kw32 = ctx_and_weights(g, "fp32")
+    hs = hotpath.HoistedState(ctx, kw)
+    lay = ctx.layout
+    hoist_cols = lay.k_pad - (hs.k_h - 512)
+    w0h = hs.w0h().float()
+    assert torch.equal(w0h[:, :512], torch.eye(512, device=DEV))
+    assert torch.equal(w0h[:, 512:], kw.w0[:, hoist_cols:].float())
+    for image in (0, 1):
+        for res, begin, count in ((32, 0, 32 ** 3), (40, 12345, 20000), (33, 77, 3000), (64, 64 * 64 * 5 + 13, 500)):
+            Xh = hs.gather_grid(image, res, begin, count).float()
+            full = hotpath.gather_grid_features(ctx, image, res, begin, count).float()
+            assert torch.equal(Xh[:, 512:], full[:, hoist_cols:]), (res, begin)
+            full32 = hotpath.gather_grid_features(ctx32, image, res, begin, count)
+            want = full32[:, :hoist_cols] @ kw32.w0[:, :hoist_cols].t()
+            err = (Xh[:, :512] - want).abs().max().item()
+            scale = want.abs().max().item()
+            print(f"addend image {image} res {res}: max err {err:.3e} (max |addend| {scale:.3f})")
+            assert err <= 2e-2 * max(scale, 1.0)
+
+
+def test_hoisted_grid_sdf_vs_oracle_and_unhoisted(monkeypatch):
+    inp = synth.make_inputs(seed=22, B=1, N=8, size="small", trans="camera")
+    ref = P.dense_grid_sdf(inp.maps, inp.vols, inp.trans_mat, inp.weights, 32, sdf_scale=10.0, chunk=8192).reshape(-1)
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "bf16")
+    hoisted = hotpath.grid_sdf(ctx, kw, 32, sdf_scale=10.0, chunk_rows=5000)[0].cpu().numpy()
+    monkeypatch.setenv("LIST_B200_HOIST", "0")
+    plain = hotpath.grid_sdf(ctx, kw, 32, sdf_scale=10.0, chunk_rows=5000)[0].cpu().numpy()
+    e_h, e_p = np.abs(hoisted - ref).max(), np.abs(plain - ref).max()
+    print(f"bf16 grid 32^3 vs oracle: hoisted {e_h:.3e}, unhoisted {e_p:.3e} (sdf/10)")
+    assert e_h <= BF16_TOL and e_p <= BF16_TOL
