@@ -24,8 +24,10 @@
 //                        (H,D)-interpolated projected columns are summed ONCE per voxel cell and a step costs one
 //                        FMA per channel and class.  State per class: G1 (column at i0+1) and D = G1 - G0, a
 //                        function of the cell only (bit-exact under any chunking / sharding of the grid).
-//   hoist_rest_kernel    the remaining feature columns (levels 32^3, 64^3, 128^3, occupancy, q, pad) exactly as
-//                        gather_grid.cu computes them, with break masks so the per-step loop is branch-free.
+//                        Steps at which a class enters a new cell are flagged in a per-step control word built
+//                        once per tile, so the walk between two such steps is a branch-free FMA loop.
+//   hoist_rest_kernel    the remaining feature columns (levels 32^3, 64^3, 128^3, occupancy, q, pad), bit-identical
+//                        to gather_grid.cu's, in two divergence-free phases through a shared-memory column table.
 #include <cstdlib>
 
 #include "hoist.cuh"
@@ -37,13 +39,46 @@ int mlp_tc_project(const ListWeights* w, int col0, int col_stride, int groups, i
 
 namespace hoist {
 
-constexpr int kPz = 64;             // points per CTA (one 64-bit break mask per walker class)
-constexpr int kMaxRuns = 4;         // z-runs one tile may touch (launcher: res >= 32)
+// Tiles never straddle z-runs: tile t = (z-line, segment of kPz steps of that line), clipped to the launch's
+// point range [begin, end).  Everything a tile computes is therefore a function of absolute grid positions
+// only, which is what makes any chunking / sharding of the grid bit-identical.
+struct TileMap {
+  int64_t line0;                    // first z-line (flat index / res) touched by [begin, end)
+  int64_t begin, end;               // flat grid range of this launch
+  int segs;                         // tiles per z-line
+  int kPz;                          // steps per tile
+  int res;
+  double bb_min, bb_max;
+};
+
+struct TileSpan {
+  int64_t g_tile0;                  // flat grid index of step 0
+  int s_lo, s_hi;                   // steps of the tile inside [begin, end)
+  float qy, qz;                     // swapped/scaled query components 1 (-> H) and 2 (-> D), constant over the tile
+};
+
+__device__ __forceinline__ bool tile_span(const TileMap& m, unsigned tile, TileSpan& t) {
+  const int64_t line = m.line0 + tile / m.segs;
+  const int gz0 = static_cast<int>(tile % m.segs) * m.kPz;
+  t.g_tile0 = line * m.res + gz0;
+  const int full = min(m.kPz, m.res - gz0);
+  t.s_lo = static_cast<int>(max(static_cast<int64_t>(0), m.begin - t.g_tile0));
+  t.s_hi = static_cast<int>(min(static_cast<int64_t>(full), m.end - t.g_tile0));
+  // reference utils.py:84-95 (x slowest, z fastest) and models.py:91-92 ([2,1,0] swap, *2)
+  t.qy = linspace_f32(static_cast<int>(line % m.res), m.res, m.bb_min, m.bb_max) * 2.0f;
+  t.qz = linspace_f32(static_cast<int>(line / m.res), m.res, m.bb_min, m.bb_max) * 2.0f;
+  return t.s_lo < t.s_hi;
+}
+__device__ __forceinline__ float step_q0(const TileMap& m, const TileSpan& t, int s) {
+  return linspace_f32(static_cast<int>(t.g_tile0 % m.res) + s, m.res, m.bb_min, m.bb_max) * 2.0f;
+}
+
+constexpr int kTile = 128;          // max steps per tile
 constexpr int kN0 = 512;            // fc_0 width == addend channels
-constexpr int kAddThreads = kN0 / 8;
-constexpr int kRestVecThreads = 128;
-constexpr int kRestThreads = kRestVecThreads + 32;
-constexpr int kRestLevels = 4;
+constexpr int kRestThreads = 256;
+constexpr int kRestLevels = 4;      // non-hoisted levels (vector ones first)
+constexpr int kMaxVec = 128;        // 16-byte items of the non-hoisted vector levels
+constexpr int kMaxTail = 64;        // tail columns: scalar levels, q, zero pad
 
 struct Corner { uint32_t base; float w; };
 
@@ -53,39 +88,45 @@ struct AddParams {
   uint32_t dstride[kMaxH];          // elements between displacement slabs
   const float* T;
   __nv_bfloat16* X;
-  int64_t ldx, N, grid_begin;
-  int S, res, nh;
+  int64_t ldx;
+  int S, nh;
   int R[kMaxH];
-  double bb_min, bb_max;
+  TileMap tm;
 };
 
 struct RestParams {
   const __nv_bfloat16* vols[kRestLevels];
   int R[kRestLevels], C[kRestLevels], xoff[kRestLevels];   // xoff: first column of the level in the hoisted row
-  int nlev;                         // levels handled here (vector levels first, then scalar ones)
-  int nvec_items;                   // 16-byte items of the vector levels (<= 128)
+  int cells_max[kRestLevels];       // table rows per (level, displacement)
+  int toff[kRestLevels];            // first float of the level's tables in shared memory
+  int nvl, nsl;                     // vector levels [0, nvl), scalar levels [nvl, nvl + nsl)
+  int nvec;                         // 16-byte items per row of the vector levels
+  int g_items;                      // phase-G items of the vector levels
   int tail0, xyz_off, k_h;          // tail region [tail0, k_h): scalar levels, q, zero pad
   __nv_bfloat16* X;
-  int64_t ldx, N, grid_begin;
-  int res;
-  double bb_min, bb_max;
+  int64_t ldx;
+  TileMap tm;
 };
 
 __device__ __forceinline__ int shift_class(int d) { return d == 1 ? 1 : (d == 2 ? 2 : 0); }
+__device__ __forceinline__ float class_shift(int cls) { return cls == 0 ? 0.f : (cls == 1 ? -kDisplacement : kDisplacement); }
+// floor(a / b) for 0 <= a < 2^20, 1 <= b < 2^10 through the float reciprocal (exact in that range)
+__device__ __forceinline__ int fast_div(int a, float inv_b) { return static_cast<int>((static_cast<float>(a) + 0.5f) * inv_b); }
 
-// grid index -> swapped/scaled query (reference utils.py:84-95, models.py:91-92)
-__device__ __forceinline__ void grid_query(int64_t g, int res, double lo, double hi, float q[3], int& gz) {
-  gz = static_cast<int>(g % res);
-  const float rx = linspace_f32(static_cast<int>(g / (static_cast<int64_t>(res) * res)), res, lo, hi);
-  const float ry = linspace_f32(static_cast<int>((g / res) % res), res, lo, hi);
-  const float rz = linspace_f32(gz, res, lo, hi);
-  q[0] = rz * 2.0f; q[1] = ry * 2.0f; q[2] = rx * 2.0f;
-}
-
-__device__ __forceinline__ int run_len(uint64_t mask, int s, int npts) {
-  const uint64_t rest = (s + 1 < 64) ? (mask >> (s + 1)) : 0ull;
-  const int n = rest ? __ffsll(static_cast<long long>(rest)) : 64;
-  return min(n, npts - s);
+// (H, D) corners and weights of displacement d for a tile (same arithmetic as gather_grid.cu)
+__device__ __forceinline__ void tile_corners(float qy, float qz, int d, int R, uint32_t row_elems, uint32_t base[4], float wyz[4]) {
+  const float q[3] = {0.f, qy, qz};
+  float pd[3];
+  displaced(q, d, pd);
+  const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
+  const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
+  const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int tz = k >> 1, ty = k & 1;
+    base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * row_elems;
+    wyz[k] = wy[ty] * wz[tz];
+  }
 }
 
 // ------------------------------------------------------------------ W0h
@@ -124,10 +165,11 @@ __device__ __forceinline__ void storev(__nv_bfloat16* __restrict__ p, const floa
   }
 }
 
+// Projected column of one W-shift class at voxel index xv: sum over the class's displacements and their 4 (H,D)
+// corners.  corners: [7][4] of the tile and level.
 template <int CLS, int V>
 __device__ __forceinline__ void load_column(const __nv_bfloat16* __restrict__ pv, uint32_t dstride, const Corner* __restrict__ corners,
                                             int xv, int cv, float out[V]) {
-  // corners: [7][4] of the current run and level; sums the class's displacements and 4 (H,D) corners
   constexpr int nd = CLS == 0 ? 5 : 1;
   const int dlist[5] = {CLS == 0 ? 0 : CLS, 3, 4, 5, 6};
 #pragma unroll
@@ -146,165 +188,162 @@ __device__ __forceinline__ void load_column(const __nv_bfloat16* __restrict__ pv
   }
 }
 
+// Control word of a step: bits 0-5 = class c (level c/3, W-shift class c%3) enters a new voxel cell,
+// bit 6 = the 2-D sample enters a new pixel cell, bits 8-15 = steps until the next step with any of those bits.
 template <int V>
 __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p) {
-  __shared__ float s_q[kPz][3];
-  __shared__ __align__(16) float s_w[kPz][12];          // per step: w0 of the 6 classes, w00 w01 w10 w11, 2 pad
-  __shared__ int s_i0[kMaxH * 3][kPz];
-  __shared__ int s_xy[kPz];                             // y0 << 16 | x0
-  __shared__ uint64_t s_mask[kMaxH * 3 + 1];
-  __shared__ Corner s_corner[kMaxRuns][kMaxH][LIST_NUM_DISP * 4];
+  constexpr int NT = kN0 / V;
+  constexpr int NC = kMaxH * 3;
+  __shared__ __align__(16) float s_w[kTile][12];        // per step: w0 of the 6 classes, w00 w01 w10 w11, 2 pad
+  __shared__ int s_i0[NC][kTile];
+  __shared__ int s_xy[kTile];                           // y0 << 16 | x0
+  __shared__ uint32_t s_ctl[kTile];
+  __shared__ uint32_t s_any[kTile / 32];
+  __shared__ Corner s_corner[kMaxH][LIST_NUM_DISP * 4];
   const int tid = threadIdx.x;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kPz;
-  const int npts = static_cast<int>(min64(kPz, p.N - n0));
-  const int64_t g0 = p.grid_begin + n0;
-  const int gz0 = static_cast<int>(g0 % p.res);
-  const int nruns = (gz0 + npts - 1) / p.res + 1;
+  TileSpan t;
+  if (!tile_span(p.tm, blockIdx.x, t)) return;
 
-  // ---- phase 0a: query, 2-D cell and weights ----
-  if (tid < kPz) {
-    float q[3] = {0.f, 0.f, 0.f};
-    int gz = 0;
-    if (tid < npts) grid_query(g0 + tid, p.res, p.bb_min, p.bb_max, q, gz);
-    s_q[tid][0] = q[0]; s_q[tid][1] = q[1]; s_q[tid][2] = q[2];
-    float ix, iy, h[3];
-    localise(q, p.T, p.S, ix, iy, h);
+  // ---- phase 0a: per step 2-D cell / weights and voxel index / weight of every class ----
+  for (int s = tid; s < kTile; s += NT) {
     int x0 = 0, y0 = 0;
     float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;                    // NaN grid -> all taps out of bounds
-    if (ix == ix && iy == iy) {
-      const float fx = floorf(ix), fy = floorf(iy);
-      x0 = static_cast<int>(fx); y0 = static_cast<int>(fy);
-      const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
-      const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
-      const bool okx1 = (x0 + 1) <= p.S - 1, oky1 = (y0 + 1) <= p.S - 1;
-      w00 = wx0 * wy0;
-      w01 = okx1 ? wx1 * wy0 : 0.f;
-      w10 = oky1 ? wx0 * wy1 : 0.f;
-      w11 = (okx1 && oky1) ? wx1 * wy1 : 0.f;
+    float q[3] = {0.f, t.qy, t.qz};
+    if (s >= t.s_lo && s < t.s_hi) {
+      q[0] = step_q0(p.tm, t, s);
+      float ix, iy, h[3];
+      localise(q, p.T, p.S, ix, iy, h);
+      if (ix == ix && iy == iy) {
+        const float fx = floorf(ix), fy = floorf(iy);
+        x0 = static_cast<int>(fx); y0 = static_cast<int>(fy);
+        const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+        const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+        const bool okx1 = (x0 + 1) <= p.S - 1, oky1 = (y0 + 1) <= p.S - 1;
+        w00 = wx0 * wy0;
+        w01 = okx1 ? wx1 * wy0 : 0.f;
+        w10 = oky1 ? wx0 * wy1 : 0.f;
+        w11 = (okx1 && oky1) ? wx1 * wy1 : 0.f;
+      }
     }
-    s_xy[tid] = (y0 << 16) | x0;
-    s_w[tid][6] = w00; s_w[tid][7] = w01; s_w[tid][8] = w10; s_w[tid][9] = w11;
-    s_w[tid][10] = 0.f; s_w[tid][11] = 0.f;
+    s_xy[s] = (y0 << 16) | x0;
+    s_w[s][6] = w00; s_w[s][7] = w01; s_w[s][8] = w10; s_w[s][9] = w11;
+    s_w[s][10] = 0.f; s_w[s][11] = 0.f;
 #pragma unroll
-    for (int c = 0; c < kMaxH * 3; ++c) {                               // voxel index / weight along the walk
+    for (int c = 0; c < NC; ++c) {
       const int hh = c / 3, cls = c % 3;
       int i0 = 0;
       float w0 = 0.f;
       if (hh < p.nh) {
-        const float shift = cls == 0 ? 0.f : (cls == 1 ? -kDisplacement : kDisplacement);
-        const Axis3 ax = axis_border(cls == 0 ? q[0] : q[0] + shift, p.R[hh]);
+        const Axis3 ax = axis_border(cls == 0 ? q[0] : q[0] + class_shift(cls), hh == 0 ? p.R[0] : p.R[1]);
         i0 = ax.i0; w0 = ax.w0;
       }
-      s_i0[c][tid] = i0;
-      s_w[tid][c] = w0;
+      s_i0[c][s] = i0;
+      s_w[s][c] = w0;
     }
   }
+  if (tid < p.nh * LIST_NUM_DISP) {                                      // (H,D) corners per (level, displacement)
+    const int d = tid % LIST_NUM_DISP, hh = tid / LIST_NUM_DISP;
+    uint32_t base[4];
+    float wyz[4];
+    tile_corners(t.qy, t.qz, d, hh == 0 ? p.R[0] : p.R[1], kN0, base, wyz);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_corner[hh][d * 4 + k] = Corner{base[k], wyz[k]};
+  }
   __syncthreads();
-  // ---- phase 0b: break masks (a step whose cell differs from the previous step's, or starts a z-run) ----
-  if (tid < kPz) {
-    const int s = tid;
-    const bool fresh = s == 0 || ((gz0 + s) % p.res) == 0;
+  // ---- phase 0b: control words ----
+  uint32_t myctl[kTile / NT];
 #pragma unroll
-    for (int c = 0; c < kMaxH * 3; ++c) {
-      const bool brk = s < npts && (fresh || s_i0[c][s] != s_i0[c][s - 1]);
-      const uint32_t b = __ballot_sync(0xffffffffu, brk);
-      if ((tid & 31) == 0) reinterpret_cast<uint32_t*>(&s_mask[c])[tid >> 5] = b;
-    }
-    const bool brk2 = s < npts && (s == 0 || s_xy[s] != s_xy[s - 1]);
-    const uint32_t b2 = __ballot_sync(0xffffffffu, brk2);
-    if ((tid & 31) == 0) reinterpret_cast<uint32_t*>(&s_mask[kMaxH * 3])[tid >> 5] = b2;
-    // (H,D) corners and weights per (run, level, displacement)
-    if (tid < nruns * p.nh * LIST_NUM_DISP) {
-      const int d = tid % LIST_NUM_DISP, hh = (tid / LIST_NUM_DISP) % p.nh, r = tid / (LIST_NUM_DISP * p.nh);
-      const int s0 = max(0, r * p.res - gz0);                            // first step of run r inside the tile
-      const float q[3] = {s_q[s0][0], s_q[s0][1], s_q[s0][2]};
-      float pd[3];
-      displaced(q, d, pd);
-      const int R = hh == 0 ? p.R[0] : p.R[1];
-      const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
-      const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
-      const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
+  for (int it = 0; it < kTile / NT; ++it) {
+    const int s = tid + it * NT;
+    uint32_t ctl = 0;
+    if (s >= t.s_lo && s < t.s_hi) {
+      const bool first = s == t.s_lo;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int tz = k >> 1, ty = k & 1;
-        Corner c;
-        c.base = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * kN0;
-        c.w = wy[ty] * wz[tz];
-        s_corner[r][hh][d * 4 + k] = c;
-      }
+      for (int c = 0; c < NC; ++c)
+        if (c / 3 < p.nh && (first || s_i0[c][s] != s_i0[c][s - 1])) ctl |= 1u << c;
+      if (first || s_xy[s] != s_xy[s - 1]) ctl |= 1u << 6;
     }
+    myctl[it] = ctl;
+    const uint32_t b = __ballot_sync(0xffffffffu, ctl != 0);
+    if ((tid & 31) == 0) s_any[s >> 5] = b;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < kTile / NT; ++it) {
+    const int s = tid + it * NT;
+    int nxt = kTile - s;                                                 // steps to the next break (clipped to s_hi later)
+    const int w = s >> 5, bit = s & 31;
+    const uint32_t rest = bit == 31 ? 0u : (s_any[w] >> (bit + 1));
+    if (rest) nxt = __ffs(rest);
+    else {
+      for (int w2 = w + 1; w2 < kTile / 32; ++w2)
+        if (s_any[w2]) { nxt = w2 * 32 + __ffs(s_any[w2]) - 1 - s; break; }
+    }
+    s_ctl[s] = myctl[it] | (static_cast<uint32_t>(nxt) << 8);
   }
   __syncthreads();
 
   const int cv = tid;
-  uint64_t m[kMaxH * 3 + 1], many = 0;
-#pragma unroll
-  for (int c = 0; c <= kMaxH * 3; ++c) {
-    m[c] = (c < kMaxH * 3 && c / 3 >= p.nh) ? 0ull : s_mask[c];
-    many |= m[c];
-  }
-  float G1[kMaxH * 3][V], D[kMaxH * 3][V], gsum[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) gsum[j] = 0.f;
+  float G1[NC][V], D[NC][V], gsum[V];
   float v00[V], v01[V], v10[V], v11[V];
-  int cur[kMaxH * 3];
+  int cur[NC];
 #pragma unroll
-  for (int c = 0; c < kMaxH * 3; ++c) {
+  for (int c = 0; c < NC; ++c) {
     cur[c] = -2;
 #pragma unroll
     for (int j = 0; j < V; ++j) { G1[c][j] = 0.f; D[c][j] = 0.f; }
   }
 #pragma unroll
-  for (int j = 0; j < V; ++j) { v00[j] = v01[j] = v10[j] = v11[j] = 0.f; }
+  for (int j = 0; j < V; ++j) { v00[j] = v01[j] = v10[j] = v11[j] = 0.f; gsum[j] = 0.f; }
 
-  __nv_bfloat16* __restrict__ dst = p.X + n0 * p.ldx + cv * V;
+  __nv_bfloat16* __restrict__ dst = p.X + (t.g_tile0 + t.s_lo - p.tm.begin) * p.ldx + cv * V;
   const int lim = p.S - 1;
-  int s = 0;
-  while (s < npts) {
-    const bool fresh = s == 0 || ((gz0 + s) % p.res) == 0;
-    const int run = (gz0 + s) / p.res;
-    bool any3 = false;
+  int s = t.s_lo;
+  while (s < t.s_hi) {
+    const uint32_t ctl = s_ctl[s];
+    if (ctl & 0x3fu) {
+      const bool first = s == t.s_lo;
 #pragma unroll
-    for (int c = 0; c < kMaxH * 3; ++c) {
-      if ((m[c] >> s) & 1ull) {
-        any3 = true;
-        const int hh = c / 3;
-        const int R = p.R[hh];
-        const int i0 = s_i0[c][s];
-        const int i1 = min(i0 + 1, R - 1);
-        const Corner* corners = s_corner[run][hh];
-        float g0v[V], g1v[V];
-        if (!fresh && i0 == cur[c] + 1) {
+      for (int c = 0; c < NC; ++c) {
+        if (ctl & (1u << c)) {
+          const int hh = c / 3;
+          const int R = hh == 0 ? p.R[0] : p.R[1];
+          const int i0 = s_i0[c][s];
+          const int i1 = min(i0 + 1, R - 1);
+          const Corner* corners = s_corner[hh];
+          const __nv_bfloat16* pv = hh == 0 ? p.pvol[0] : p.pvol[1];
+          const uint32_t ds = hh == 0 ? p.dstride[0] : p.dstride[1];
+          float g0v[V], g1v[V];
+          if (!first && i0 == cur[c] + 1) {
 #pragma unroll
-          for (int j = 0; j < V; ++j) g0v[j] = G1[c][j];
-        } else {
-          if (c % 3 == 0) load_column<0, V>(p.pvol[hh], p.dstride[hh], corners, i0, cv, g0v);
-          else if (c % 3 == 1) load_column<1, V>(p.pvol[hh], p.dstride[hh], corners, i0, cv, g0v);
-          else load_column<2, V>(p.pvol[hh], p.dstride[hh], corners, i0, cv, g0v);
+            for (int j = 0; j < V; ++j) g0v[j] = G1[c][j];
+          } else {
+            if (c % 3 == 0) load_column<0, V>(pv, ds, corners, i0, cv, g0v);
+            else if (c % 3 == 1) load_column<1, V>(pv, ds, corners, i0, cv, g0v);
+            else load_column<2, V>(pv, ds, corners, i0, cv, g0v);
+          }
+          if (i1 != i0) {
+            if (c % 3 == 0) load_column<0, V>(pv, ds, corners, i1, cv, g1v);
+            else if (c % 3 == 1) load_column<1, V>(pv, ds, corners, i1, cv, g1v);
+            else load_column<2, V>(pv, ds, corners, i1, cv, g1v);
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) g1v[j] = g0v[j];
+          }
+#pragma unroll
+          for (int j = 0; j < V; ++j) { D[c][j] = g1v[j] - g0v[j]; G1[c][j] = g1v[j]; }
+          cur[c] = i0;
         }
-        if (i1 != i0) {
-          if (c % 3 == 0) load_column<0, V>(p.pvol[hh], p.dstride[hh], corners, i1, cv, g1v);
-          else if (c % 3 == 1) load_column<1, V>(p.pvol[hh], p.dstride[hh], corners, i1, cv, g1v);
-          else load_column<2, V>(p.pvol[hh], p.dstride[hh], corners, i1, cv, g1v);
-        } else {
-#pragma unroll
-          for (int j = 0; j < V; ++j) g1v[j] = g0v[j];
-        }
-#pragma unroll
-        for (int j = 0; j < V; ++j) { D[c][j] = g1v[j] - g0v[j]; G1[c][j] = g1v[j]; }
-        cur[c] = i0;
       }
-    }
-    if (any3) {
 #pragma unroll
       for (int j = 0; j < V; ++j) {
         float a = G1[0][j];
 #pragma unroll
-        for (int c = 1; c < kMaxH * 3; ++c) a += G1[c][j];
+        for (int c = 1; c < NC; ++c) a += G1[c][j];
         gsum[j] = a;
       }
     }
-    if ((m[kMaxH * 3] >> s) & 1ull) {
+    if (ctl & 0x40u) {
       const int xy = s_xy[s];
       const int cx = xy & 0xffff, cy = xy >> 16;
       const int x1 = min(cx + 1, lim), y1 = min(cy + 1, lim);
@@ -314,13 +353,13 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
       loadv<V>(pm + (static_cast<size_t>(y1) * p.S + cx) * kN0, v10);
       loadv<V>(pm + (static_cast<size_t>(y1) * p.S + x1) * kN0, v11);
     }
-    const int n = run_len(many, s, npts);
+    const int n = min(static_cast<int>((ctl >> 8) & 0xffu), t.s_hi - s);
 #pragma unroll 2
     for (int k = 0; k < n; ++k, ++s, dst += p.ldx) {
       const float4 wa = *reinterpret_cast<const float4*>(&s_w[s][0]);
       const float4 wb = *reinterpret_cast<const float4*>(&s_w[s][4]);
       const float2 wc = *reinterpret_cast<const float2*>(&s_w[s][8]);
-      const float w3[kMaxH * 3] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y};
+      const float w3[NC] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y};
       float acc[V];
 #pragma unroll
       for (int j = 0; j < V; ++j) {
@@ -329,7 +368,7 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
         a = fmaf(v10[j], wc.x, a);
         a = fmaf(v11[j], wc.y, a);
 #pragma unroll
-        for (int c = 0; c < kMaxH * 3; ++c) a = fmaf(-w3[c], D[c][j], a);
+        for (int c = 0; c < NC; ++c) a = fmaf(-w3[c], D[c][j], a);
         acc[j] = a;
       }
       storev<V>(dst, acc);
@@ -338,188 +377,204 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
 }
 
 // ------------------------------------------------------------------ the remaining columns
-__device__ __forceinline__ void load_row8(const __nv_bfloat16* __restrict__ vol, const uint32_t base[4], const float wyz[4],
-                                          int xv, int C, float out[8]) {
-  float v[8];
-  load8(vol + base[0] + static_cast<uint32_t>(xv) * C, v);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) out[j] = v[j] * wyz[0];
-#pragma unroll
-  for (int k = 1; k < 4; ++k) {
-    load8(vol + base[k] + static_cast<uint32_t>(xv) * C, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) out[j] = fmaf(v[j], wyz[k], out[j]);
-  }
-}
+// Two phases per tile, both free of per-lane control flow:
+//   G: for every (level, displacement) the (H,D)-interpolated column  G[xv][c] = sum_4 (wy*wz) V[z_k][y_k][xv][c]
+//      of every voxel index xv the tile's steps touch (+ its right neighbour), fp32, into shared memory;
+//   L: out[s][col] = G[x0] + w1 * (G[x0+1] - G[x0]); one (step, 16-byte vector) item per thread, consecutive lanes
+//      write consecutive vectors of one row.
+// Same arithmetic, in the same order, as the z-run walker of gather_grid.cu, so the columns are bit-identical to it.
+struct VecDesc { int tab; int cstride; int col; int lc; };   // table base (floats), floats per cell, X column, level*3+class
 
 __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestParams p) {
-  __shared__ float s_q[kPz][3];
-  __shared__ int s_i0[kRestLevels][3][kPz];
-  __shared__ float s_w1[kRestLevels][3][kPz];
-  __shared__ uint64_t s_mask[kRestLevels][3];
+  extern __shared__ __align__(16) float s_tab[];
+  __shared__ float s_q0[kTile];
+  __shared__ int s_rel[kRestLevels][3][kTile];          // voxel index relative to the class's first one
+  __shared__ float s_w1[kRestLevels][3][kTile];
+  __shared__ int s_first[kRestLevels][3], s_ncell[kRestLevels][3];
+  __shared__ __align__(16) VecDesc s_vec[kMaxVec];
+  __shared__ int s_tailtab[kMaxTail];                   // scalar columns: table base | class << 24
   const int tid = threadIdx.x;
-  const int64_t n0 = static_cast<int64_t>(blockIdx.x) * kPz;
-  const int npts = static_cast<int>(min64(kPz, p.N - n0));
-  const int64_t g0 = p.grid_begin + n0;
-  const int gz0 = static_cast<int>(g0 % p.res);
-  __nv_bfloat16* __restrict__ Xb = p.X + n0 * p.ldx;
+  TileSpan t;
+  if (!tile_span(p.tm, blockIdx.x, t)) return;
+  const int nlev = p.nvl + p.nsl;
+  const int kPz = p.tm.kPz;
 
-  if (tid < kPz) {
-    float q[3] = {0.f, 0.f, 0.f};
-    int gz = 0;
-    if (tid < npts) grid_query(g0 + tid, p.res, p.bb_min, p.bb_max, q, gz);
-    s_q[tid][0] = q[0]; s_q[tid][1] = q[1]; s_q[tid][2] = q[2];
+  // ---- phase 0: per-step voxel index / weight per (level, class); descriptors ----
+  if (tid < nlev * 3) {
+    const int li = tid / 3, cls = tid % 3;
+    const float sh = class_shift(cls);
+    const int a = axis_border(step_q0(p.tm, t, t.s_lo) + sh, p.R[li]).i0;
+    const int b = axis_border(step_q0(p.tm, t, t.s_hi - 1) + sh, p.R[li]).i0;
+    s_first[li][cls] = a;
+    s_ncell[li][cls] = min(min(b + 1, p.R[li] - 1) - a + 1, p.cells_max[li]);
   }
-  __syncthreads();
-  for (int i = tid; i < p.nlev * 3 * kPz; i += kRestThreads) {
-    const int s = i % kPz, cls = (i / kPz) % 3, li = i / (3 * kPz);
-    const float shift = cls == 0 ? 0.f : (cls == 1 ? -kDisplacement : kDisplacement);
-    const Axis3 ax = axis_border(cls == 0 ? s_q[s][0] : s_q[s][0] + shift, p.R[li]);
-    s_i0[li][cls][s] = ax.i0;
-    s_w1[li][cls][s] = ax.w1;
-  }
-  __syncthreads();
-  for (int i = tid; i < p.nlev * 3 * kPz; i += kRestThreads) {         // 160 = 5 warps: each warp covers 32 steps of one class
-    const int s = i % kPz, cls = (i / kPz) % 3, li = i / (3 * kPz);
-    const bool fresh = s == 0 || ((gz0 + s) % p.res) == 0;
-    const bool brk = s < npts && (fresh || s_i0[li][cls][s] != s_i0[li][cls][s - 1]);
-    const uint32_t b = __ballot_sync(0xffffffffu, brk);
-    if ((tid & 31) == 0) reinterpret_cast<uint32_t*>(&s_mask[li][cls])[s >> 5] = b;
-  }
-  __syncthreads();
-
-  if (tid < kRestVecThreads) {
-    // ================= 3-D vector walker =================
-    if (tid >= p.nvec_items) return;
-    int item = tid, li = -1, d = 0, cv = 0;
-    for (int ll = 0; ll < p.nlev; ++ll) {
-      if (p.C[ll] & 7) continue;
-      const int ncv = p.C[ll] >> 3;
-      const int cnt = LIST_NUM_DISP * ncv;
-      if (item < cnt) {
-        li = ll;
-        const int di = item / ncv;
-        d = di == 0 ? 0 : (di <= 4 ? di + 2 : di - 4);                  // W-shifted displacements (1,2) last
-        cv = item % ncv;
-        break;
-      }
+  for (int s = tid; s < kPz; s += kRestThreads) s_q0[s] = (s >= t.s_lo && s < t.s_hi) ? step_q0(p.tm, t, s) : 0.f;
+  for (int v = tid; v < p.nvec; v += kRestThreads) {                    // vector item -> (level, displacement, channel vector)
+    int item = v, li = 0;
+    for (; li < p.nvl; ++li) {
+      const int cnt = LIST_NUM_DISP * (p.C[li] >> 3);
+      if (item < cnt) break;
       item -= cnt;
     }
-    if (li < 0) return;
-    const int R = p.R[li], C = p.C[li];
-    const int cls = shift_class(d);
-    const __nv_bfloat16* __restrict__ vol = p.vols[li];
-    const int* __restrict__ i0s = s_i0[li][cls];
-    const float* __restrict__ w1s = s_w1[li][cls];
-    const uint64_t m = s_mask[li][cls];
-    uint32_t base[4] = {0, 0, 0, 0};
-    float wyz[4] = {0.f, 0.f, 0.f, 0.f};
-    float G0[8], G1[8], Dv[8];
-    int cx0 = -2;
-    __nv_bfloat16* __restrict__ dst = Xb + p.xoff[li] + d * C + cv * 8;
-    int s = 0;
-    while (s < npts) {
-      const bool fresh = s == 0 || ((gz0 + s) % p.res) == 0;
-      if (fresh) {                                       // new (x, y) run: (H, D) corners and weights
-        const float q[3] = {s_q[s][0], s_q[s][1], s_q[s][2]};
-        float pd[3];
-        displaced(q, d, pd);
-        const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
-        const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
-        const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int tz = k >> 1, ty = k & 1;
-          base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * C + cv * 8;
-          wyz[k] = wy[ty] * wz[tz];
-        }
-      }
-      const int i0 = i0s[s];
-      const int i1 = min(i0 + 1, R - 1);
-      if (!fresh && i0 == cx0 + 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) G0[j] = G1[j];
-      } else {
-        load_row8(vol, base, wyz, i0, C, G0);
-      }
-      if (i1 != i0) load_row8(vol, base, wyz, i1, C, G1);
-      else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) G1[j] = G0[j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) Dv[j] = G1[j] - G0[j];
-      cx0 = i0;
-      const int n = run_len(m, s, npts);
-      for (int k = 0; k < n; ++k, ++s, dst += p.ldx) {
-        const float w1 = w1s[s];
-        float out[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) out[j] = fmaf(Dv[j], w1, G0[j]);
-        store8(dst, out);
+    const int ncv = p.C[li] >> 3;
+    const int d = item / ncv, cvv = item % ncv;
+    VecDesc vd;
+    vd.tab = p.toff[li] + d * p.cells_max[li] * p.C[li] + cvv * 8;
+    vd.cstride = p.C[li];
+    vd.col = p.xoff[li] + d * p.C[li] + cvv * 8;
+    vd.lc = li * 3 + shift_class(d);
+    s_vec[v] = vd;
+  }
+  const int nscal = p.xyz_off - p.tail0;
+  for (int j = tid; j < nscal; j += kRestThreads) {                     // scalar column -> table base, class
+    const int col = p.tail0 + j;
+    int val = 0;
+    for (int li = p.nvl; li < nlev; ++li) {
+      const int rel = col - p.xoff[li];
+      if (rel >= 0 && rel < LIST_NUM_DISP * p.C[li]) {
+        const int d = rel / p.C[li], c = rel % p.C[li];
+        val = (p.toff[li] + d * p.cells_max[li] * p.C[li] + c) | ((li * 3 + shift_class(d)) << 24);
       }
     }
-  } else {
-    // ================= tail: scalar levels, q, zero pad (one warp) =================
-    const int lane = tid - kRestVecThreads;
-    const int ntail = p.k_h - p.tail0;                 // <= 64 (checked by the launcher)
-    const int nscal = p.xyz_off - p.tail0;             // scalar-level columns, <= 29
-    int li = -1, d = 0, c = 0;
-    if (lane < nscal) {
-      const int colabs = p.tail0 + lane;
-      for (int ll = 0; ll < p.nlev; ++ll) {
-        if (!(p.C[ll] & 7)) continue;
-        const int rel = colabs - p.xoff[ll];
-        if (rel >= 0 && rel < LIST_NUM_DISP * p.C[ll]) { li = ll; d = rel / p.C[ll]; c = rel % p.C[ll]; }
+    s_tailtab[j] = val;
+  }
+  __syncthreads();
+  for (int i = tid; i < nlev * 3 * kPz; i += kRestThreads) {
+    const int s = i % kPz, lc = i / kPz;
+    const int li = lc / 3, cls = lc % 3;
+    int rel = 0;
+    float w1 = 0.f;
+    if (s >= t.s_lo && s < t.s_hi) {
+      const Axis3 ax = axis_border(cls == 0 ? s_q0[s] : s_q0[s] + class_shift(cls), p.R[li]);
+      rel = min(ax.i0 - s_first[li][cls], p.cells_max[li] - 1);
+      w1 = ax.w1;
+    }
+    s_rel[li][cls][s] = rel;
+    s_w1[li][cls][s] = w1;
+  }
+
+  // ---- phase G: vector levels ----
+  {
+    int lvl_begin = 0;
+    for (int li = 0; li < p.nvl; ++li) {
+      const int C = p.C[li], ncv = C >> 3, cm = p.cells_max[li];
+      const int per_d = cm * ncv, cnt = LIST_NUM_DISP * per_d;
+      const float inv_per_d = 1.0f / static_cast<float>(per_d), inv_ncv = 1.0f / static_cast<float>(ncv);
+      const __nv_bfloat16* __restrict__ vol = p.vols[li];
+      // first item of this level owned by the thread: items are striped over the CTA across all levels
+      int it = tid - (lvl_begin % kRestThreads);
+      if (it < 0) it += kRestThreads;
+      for (; it < cnt; it += kRestThreads) {
+        const int d = fast_div(it, inv_per_d);
+        const int rem = it - d * per_d;
+        const int c = fast_div(rem, inv_ncv);
+        const int cvv = rem - c * ncv;
+        const int cls = shift_class(d);
+        if (c >= s_ncell[li][cls]) continue;
+        const int xv = s_first[li][cls] + c;
+        uint32_t base[4];
+        float wyz[4];
+        tile_corners(t.qy, t.qz, d, p.R[li], static_cast<uint32_t>(C), base, wyz);
+        const __nv_bfloat16* src = vol + static_cast<uint32_t>(xv) * C + cvv * 8;
+        float v[8], g[8];
+        load8(src + base[0], v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = v[j] * wyz[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+          load8(src + base[k], v);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = fmaf(v[j], wyz[k], g[j]);
+        }
+        float* dstt = s_tab + p.toff[li] + (d * cm + c) * C + cvv * 8;
+        *reinterpret_cast<float4*>(dstt) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(dstt + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      }
+      lvl_begin += cnt;
+    }
+    // scalar levels (C % 8 != 0): one (displacement, cell, channel) value per item
+    for (int li = p.nvl; li < nlev; ++li) {
+      const int C = p.C[li], cm = p.cells_max[li];
+      const int per_d = cm * C, cnt = LIST_NUM_DISP * per_d;
+      const float inv_per_d = 1.0f / static_cast<float>(per_d), inv_c = 1.0f / static_cast<float>(C);
+      const __nv_bfloat16* __restrict__ vol = p.vols[li];
+      for (int it = tid; it < cnt; it += kRestThreads) {
+        const int d = fast_div(it, inv_per_d);
+        const int rem = it - d * per_d;
+        const int c = fast_div(rem, inv_c);
+        const int ch = rem - c * C;
+        const int cls = shift_class(d);
+        if (c >= s_ncell[li][cls]) continue;
+        const int xv = s_first[li][cls] + c;
+        uint32_t base[4];
+        float wyz[4];
+        tile_corners(t.qy, t.qz, d, p.R[li], static_cast<uint32_t>(C), base, wyz);
+        const __nv_bfloat16* src = vol + static_cast<uint32_t>(xv) * C + ch;
+        float r = __bfloat162float(src[base[0]]) * wyz[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) r = fmaf(__bfloat162float(src[base[k]]), wyz[k], r);
+        s_tab[p.toff[li] + (d * cm + c) * C + ch] = r;
       }
     }
-    const int R = li >= 0 ? p.R[li] : 1, C = li >= 0 ? p.C[li] : 1;
-    const __nv_bfloat16* __restrict__ vol = li >= 0 ? p.vols[li] : nullptr;
-    const int cls = shift_class(d);
-    const int lsel = li >= 0 ? li : 0;
-    uint32_t base[4] = {0, 0, 0, 0};
-    float wyz[4] = {0.f, 0.f, 0.f, 0.f};
-    float g0 = 0.f, g1 = 0.f;
-    int cx0 = -2;
-    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-    for (int s = 0; s < npts; ++s) {
-      float val = 0.f;
-      if (li >= 0) {
-        const int i0 = s_i0[lsel][cls][s];
-        const bool fresh = s == 0 || ((gz0 + s) % p.res) == 0;
-        if (fresh) {
-          const float q[3] = {s_q[s][0], s_q[s][1], s_q[s][2]};
-          float pd[3];
-          displaced(q, d, pd);
-          const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
-          const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
-          const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
+  }
+  __syncthreads();
+
+  // ---- phase L: vector columns ----
+  const int nsteps = t.s_hi - t.s_lo;
+  __nv_bfloat16* __restrict__ Xb = p.X + (t.g_tile0 + t.s_lo - p.tm.begin) * p.ldx;
+  {
+    const float inv_nvec = 1.0f / static_cast<float>(p.nvec);
+    const int total = nsteps * p.nvec;
+    for (int it = tid; it < total; it += kRestThreads) {
+      const int sr = fast_div(it, inv_nvec);
+      const int v = it - sr * p.nvec;
+      const int s = t.s_lo + sr;
+      const VecDesc vd = s_vec[v];
+      const int li = vd.lc / 3, cls = vd.lc - li * 3;
+      const int c = s_rel[li][cls][s];
+      const float w1 = s_w1[li][cls][s];
+      const int c1 = min(c + 1, s_ncell[li][cls] - 1);
+      const float* g0p = s_tab + vd.tab + c * vd.cstride;
+      const float* g1p = s_tab + vd.tab + c1 * vd.cstride;
+      const float4 a0 = *reinterpret_cast<const float4*>(g0p), a1 = *reinterpret_cast<const float4*>(g0p + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(g1p), b1 = *reinterpret_cast<const float4*>(g1p + 4);
+      float out[8];
+      out[0] = fmaf(b0.x - a0.x, w1, a0.x); out[1] = fmaf(b0.y - a0.y, w1, a0.y);
+      out[2] = fmaf(b0.z - a0.z, w1, a0.z); out[3] = fmaf(b0.w - a0.w, w1, a0.w);
+      out[4] = fmaf(b1.x - a1.x, w1, a1.x); out[5] = fmaf(b1.y - a1.y, w1, a1.y);
+      out[6] = fmaf(b1.z - a1.z, w1, a1.z); out[7] = fmaf(b1.w - a1.w, w1, a1.w);
+      store8(Xb + static_cast<int64_t>(sr) * p.ldx + vd.col, out);
+    }
+  }
+  // ---- tail: scalar levels, q, zero pad; one (step, 8-column group) item per thread ----
+  {
+    const int ngrp = (p.k_h - p.tail0) >> 3;             // tail0 and k_h are multiples of 8
+    const float inv_ngrp = 1.0f / static_cast<float>(ngrp);
+    const int total = nsteps * ngrp;
+    for (int it = tid; it < total; it += kRestThreads) {
+      const int sr = fast_div(it, inv_ngrp);
+      const int gq = it - sr * ngrp;
+      const int s = t.s_lo + sr;
+      float out[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int tz = k >> 1, ty = k & 1;
-            base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * C + c;
-            wyz[k] = wy[ty] * wz[tz];
-          }
+      for (int j = 0; j < 8; ++j) {
+        const int col = gq * 8 + j;                      // relative to tail0
+        float val = 0.f;
+        if (col < nscal) {
+          const int tt = s_tailtab[col];
+          const int lc = tt >> 24, tab = tt & 0xffffff;
+          const int li = lc / 3, cls = lc - li * 3;
+          const int c = s_rel[li][cls][s];
+          const int c1 = min(c + 1, s_ncell[li][cls] - 1);
+          const float g0 = s_tab[tab + c * p.C[li]], g1 = s_tab[tab + c1 * p.C[li]];
+          val = fmaf(g1 - g0, s_w1[li][cls][s], g0);
+        } else if (col < nscal + 3) {
+          const int a = col - nscal;
+          val = a == 0 ? s_q0[s] : (a == 1 ? t.qy : t.qz);
         }
-        if (fresh || i0 != cx0) {
-          auto row = [&](int xv) {
-            float r = __bfloat162float(vol[base[0] + static_cast<uint32_t>(xv) * C]) * wyz[0];
-#pragma unroll
-            for (int k = 1; k < 4; ++k) r = fmaf(__bfloat162float(vol[base[k] + static_cast<uint32_t>(xv) * C]), wyz[k], r);
-            return r;
-          };
-          const int i1 = min(i0 + 1, R - 1);
-          g0 = (!fresh && i0 == cx0 + 1) ? g1 : row(i0);
-          g1 = (i1 != i0) ? row(i1) : g0;
-          cx0 = i0;
-        }
-        val = fmaf(g1 - g0, s_w1[lsel][cls][s], g0);
-      } else if (lane >= nscal && lane < nscal + 3) {
-        val = s_q[s][lane - nscal];
+        out[j] = val;
       }
-      __nv_bfloat16* row_out = Xb + static_cast<int64_t>(s) * p.ldx + p.tail0;
-      if (lane < ntail) row_out[lane] = __float2bfloat16_rn(val);
-      if (lane + 32 < ntail) row_out[lane + 32] = zero;   // columns beyond nscal+3 are padding (nscal+3 <= 32)
+      store8(Xb + static_cast<int64_t>(sr) * p.ldx + p.tail0 + gq * 8, out);
     }
   }
 }
@@ -582,14 +637,14 @@ int prepare(const ListCtx* ctx, const ListWeights* w, const Plan& pl, void* buf,
   return LIST_OK;
 }
 
-// The non-hoisted levels / tail of the row for hoist_rest_kernel; LIST_ENOSYS if the mapping does not fit.
-static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay, int image, RestParams* out) {
+// Tile size and shared-memory plan of hoist_rest_kernel for a res^3 grid; LIST_ENOSYS if the mapping does not fit.
+static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay, int image, int res, RestParams* out, size_t* smem) {
   RestParams& r = *out;
-  int nl = 0, items = 0;
   const int shift = pl.hoist_cols - kN0;               // column in the full layout -> column in the hoisted row
   bool hoisted[LIST_MAX_LEVELS] = {};
   for (int h = 0; h < pl.nh; ++h) hoisted[pl.lev[h]] = true;
-  int tail0 = lay.xyz_off;
+  int nl = 0, tail0 = lay.xyz_off;
+  r.nvl = r.nsl = r.nvec = 0;
   for (int pass = 0; pass < 2; ++pass) {               // vector levels (layout order) first, then scalar levels
     for (int l = ctx->n_levels - 1; l >= 0; --l) {
       if (hoisted[l]) continue;
@@ -602,36 +657,70 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       r.R[nl] = ctx->vol_res[l];
       r.C[nl] = ctx->vol_ch[l];
       r.xoff[nl] = lay.vol_off[l] - shift;
-      if (vec) items += LIST_NUM_DISP * (ctx->vol_ch[l] / 8);
-      else if (lay.vol_off[l] < tail0) tail0 = lay.vol_off[l];
+      if (vec) { r.nvec += LIST_NUM_DISP * (ctx->vol_ch[l] / 8); ++r.nvl; }
+      else { if (lay.vol_off[l] < tail0) tail0 = lay.vol_off[l]; ++r.nsl; }
       ++nl;
     }
   }
-  if (items > kRestVecThreads) return LIST_ENOSYS;
-  r.nlev = nl;
-  r.nvec_items = items;
+  if (r.nvec > kMaxVec || r.nvec == 0) return LIST_ENOSYS;
   r.tail0 = tail0 - shift;
   r.xyz_off = lay.xyz_off - shift;
   r.k_h = pl.k_h;
-  if (r.xyz_off + 3 - r.tail0 > 32 || r.k_h - r.tail0 > 64) return LIST_ENOSYS;
-  return LIST_OK;
+  if (r.tail0 % 8 != 0 || r.k_h - r.tail0 > kMaxTail || r.xyz_off + 3 > r.k_h) return LIST_ENOSYS;
+  // the vector columns must be exactly [kN0, tail0): the kernel writes nothing else there
+  if (kN0 + r.nvec * 8 != r.tail0) return LIST_ENOSYS;
+  // largest tile whose column tables fit next to a second CTA on the SM
+  for (int kpz = kTile; kpz >= 16; kpz >>= 1) {
+    size_t floats = 0;
+    int items = 0;
+    for (int i = 0; i < nl; ++i) {
+      const int span = res > 1 ? static_cast<int>((static_cast<int64_t>(kpz - 1) * (r.R[i] - 1)) / (res - 1)) : 0;
+      int cm = span + 3;
+      if (cm > r.R[i]) cm = r.R[i];
+      r.cells_max[i] = cm;
+      r.toff[i] = static_cast<int>(floats);
+      floats += static_cast<size_t>(LIST_NUM_DISP) * cm * r.C[i];
+      if (i < r.nvl) items += LIST_NUM_DISP * cm * (r.C[i] / 8);
+    }
+    if (floats * 4 <= 96 * 1024 && floats < (1u << 24) && items < (1 << 20)) {
+      r.g_items = items;
+      r.tm.kPz = kpz;
+      *smem = floats * 4;
+      return LIST_OK;
+    }
+  }
+  return LIST_ENOSYS;
+}
+
+static void fill_tilemap(TileMap* tm, int res, double bb_min, double bb_max, int64_t begin, int64_t count, int kpz) {
+  tm->line0 = begin / res;
+  tm->begin = begin;
+  tm->end = begin + count;
+  tm->kPz = kpz;
+  tm->segs = (res + kpz - 1) / kpz;
+  tm->res = res;
+  tm->bb_min = bb_min;
+  tm->bb_max = bb_max;
+}
+static unsigned tile_count(const TileMap& tm) {
+  const int64_t lines = (tm.end - 1) / tm.res - tm.line0 + 1;
+  return static_cast<unsigned>(lines * tm.segs);
 }
 
 // LIST_OK if gather() covers a res^3 grid of this configuration.
 int check_gather(const ListCtx* ctx, const Plan& pl, int res) {
-  if ((res - 1 + kPz - 1) / res + 1 > kMaxRuns) return LIST_ENOSYS;
   ListLayout lay;
   const int rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr);
   if (rc) return rc;
   RestParams r{};
-  return build_rest(ctx, pl, lay, 0, &r);
+  size_t smem = 0;
+  return build_rest(ctx, pl, lay, 0, res, &r, &smem);
 }
 
 // Feature rows X_h[count][ldx] of grid points [begin, begin+count) of image `image`.
 int gather(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max,
            int64_t begin, int64_t count, void* X, int64_t ldx, cudaStream_t st) {
   if (count == 0) return LIST_OK;
-  if ((res - 1 + kPz - 1) / res + 1 > kMaxRuns) return LIST_ENOSYS;
   ListLayout lay;
   const int rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr);
   if (rc) return rc;
@@ -649,30 +738,23 @@ int gather(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int r
   a.T = ctx->trans_mat + image * 12;
   a.X = static_cast<__nv_bfloat16*>(X);
   a.ldx = ldx;
-  a.N = count;
-  a.grid_begin = begin;
   a.S = ctx->map_size;
-  a.res = res;
-  a.bb_min = bb_min;
-  a.bb_max = bb_max;
+  fill_tilemap(&a.tm, res, bb_min, bb_max, begin, count, kTile);
 
   RestParams r{};
-  const int rc2 = build_rest(ctx, pl, lay, image, &r);
+  size_t smem = 0;
+  const int rc2 = build_rest(ctx, pl, lay, image, res, &r, &smem);
   if (rc2) return rc2;
   r.X = a.X;
   r.ldx = ldx;
-  r.N = count;
-  r.grid_begin = begin;
-  r.res = res;
-  r.bb_min = bb_min;
-  r.bb_max = bb_max;
+  fill_tilemap(&r.tm, res, bb_min, bb_max, begin, count, r.tm.kPz);
 
-  const unsigned tiles = static_cast<unsigned>((count + kPz - 1) / kPz);
   static const int vec = []() { const char* e = getenv("LIST_B200_HOIST_VEC"); return (e && e[0] == '8') ? 8 : 4; }();
-  if (vec == 8) hoist_addend_kernel<8><<<tiles, kN0 / 8, 0, st>>>(a);
-  else hoist_addend_kernel<4><<<tiles, kN0 / 4, 0, st>>>(a);
+  if (vec == 8) hoist_addend_kernel<8><<<tile_count(a.tm), kN0 / 8, 0, st>>>(a);
+  else hoist_addend_kernel<4><<<tile_count(a.tm), kN0 / 4, 0, st>>>(a);
   LIST_LAUNCH_CHECK("hoist_addend_kernel");
-  hoist_rest_kernel<<<tiles, kRestThreads, 0, st>>>(r);
+  LIST_CUDA(cudaFuncSetAttribute(hoist_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  hoist_rest_kernel<<<tile_count(r.tm), kRestThreads, smem, st>>>(r);
   LIST_LAUNCH_CHECK("hoist_rest_kernel");
   return LIST_OK;
 }
