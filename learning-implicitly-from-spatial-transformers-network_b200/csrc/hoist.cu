@@ -377,11 +377,12 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
 }
 
 // ------------------------------------------------------------------ the remaining columns
-// Two phases per tile, both free of per-lane control flow:
+// Two phases per tile:
 //   G: for every (level, displacement) the (H,D)-interpolated column  G[xv][c] = sum_4 (wy*wz) V[z_k][y_k][xv][c]
 //      of every voxel index xv the tile's steps touch (+ its right neighbour), fp32, into shared memory;
-//   L: out[s][col] = G[x0] + w1 * (G[x0+1] - G[x0]); one (step, 16-byte vector) item per thread, consecutive lanes
-//      write consecutive vectors of one row.
+//   L: out[s][col] = G[x0] + w1 * (G[x0+1] - G[x0]); a thread owns one 16-byte vector of the row and a contiguous
+//      block of steps, keeps (G[x0], G[x0+1]-G[x0]) in registers and refreshes them from the table when x0 moves;
+//      consecutive lanes write consecutive vectors of one row.
 // Same arithmetic, in the same order, as the z-run walker of gather_grid.cu, so the columns are bit-identical to it.
 struct VecDesc { int tab; int cstride; int col; int lc; };   // table base (floats), floats per cell, X column, level*3+class
 
@@ -391,15 +392,16 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   __shared__ int s_rel[kRestLevels][3][kTile];          // voxel index relative to the class's first one
   __shared__ float s_w1[kRestLevels][3][kTile];
   __shared__ int s_first[kRestLevels][3], s_ncell[kRestLevels][3];
+  __shared__ Corner s_cor[kRestLevels * LIST_NUM_DISP][4];
   __shared__ __align__(16) VecDesc s_vec[kMaxVec];
-  __shared__ int s_tailtab[kMaxTail];                   // scalar columns: table base | class << 24
+  __shared__ int s_tailtab[kMaxTail];                   // scalar columns: table base | (level*3+class) << 24
   const int tid = threadIdx.x;
   TileSpan t;
   if (!tile_span(p.tm, blockIdx.x, t)) return;
   const int nlev = p.nvl + p.nsl;
   const int kPz = p.tm.kPz;
 
-  // ---- phase 0: per-step voxel index / weight per (level, class); descriptors ----
+  // ---- phase 0: per-step voxel index / weight per (level, class); corners; descriptors ----
   if (tid < nlev * 3) {
     const int li = tid / 3, cls = tid % 3;
     const float sh = class_shift(cls);
@@ -407,6 +409,13 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     const int b = axis_border(step_q0(p.tm, t, t.s_hi - 1) + sh, p.R[li]).i0;
     s_first[li][cls] = a;
     s_ncell[li][cls] = min(min(b + 1, p.R[li] - 1) - a + 1, p.cells_max[li]);
+  } else if (tid >= 32 && tid < 32 + nlev * LIST_NUM_DISP) {
+    const int pr = tid - 32, li = pr / LIST_NUM_DISP, d = pr % LIST_NUM_DISP;
+    uint32_t base[4];
+    float wyz[4];
+    tile_corners(t.qy, t.qz, d, p.R[li], static_cast<uint32_t>(p.C[li]), base, wyz);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_cor[pr][k] = Corner{base[k], wyz[k]};
   }
   for (int s = tid; s < kPz; s += kRestThreads) s_q0[s] = (s >= t.s_lo && s < t.s_hi) ? step_q0(p.tm, t, s) : 0.f;
   for (int v = tid; v < p.nvec; v += kRestThreads) {                    // vector item -> (level, displacement, channel vector)
@@ -453,40 +462,38 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     s_w1[li][cls][s] = w1;
   }
 
-  // ---- phase G: vector levels ----
+  // ---- phase G: vector levels (items striped over the CTA across all levels) ----
   {
     int lvl_begin = 0;
     for (int li = 0; li < p.nvl; ++li) {
       const int C = p.C[li], ncv = C >> 3, cm = p.cells_max[li];
+      const int ncv_shift = 31 - __clz(ncv);                            // C / 8 is a power of two (checked by the launcher)
       const int per_d = cm * ncv, cnt = LIST_NUM_DISP * per_d;
-      const float inv_per_d = 1.0f / static_cast<float>(per_d), inv_ncv = 1.0f / static_cast<float>(ncv);
+      const float inv_per_d = 1.0f / static_cast<float>(per_d);
       const __nv_bfloat16* __restrict__ vol = p.vols[li];
-      // first item of this level owned by the thread: items are striped over the CTA across all levels
+      float* __restrict__ tab = s_tab + p.toff[li];
+      const int* first = s_first[li];
+      const int* ncell = s_ncell[li];
       int it = tid - (lvl_begin % kRestThreads);
       if (it < 0) it += kRestThreads;
       for (; it < cnt; it += kRestThreads) {
         const int d = fast_div(it, inv_per_d);
         const int rem = it - d * per_d;
-        const int c = fast_div(rem, inv_ncv);
-        const int cvv = rem - c * ncv;
+        const int c = rem >> ncv_shift;
+        const int cvv = rem & (ncv - 1);
         const int cls = shift_class(d);
-        if (c >= s_ncell[li][cls]) continue;
-        const int xv = s_first[li][cls] + c;
-        uint32_t base[4];
-        float wyz[4];
-        tile_corners(t.qy, t.qz, d, p.R[li], static_cast<uint32_t>(C), base, wyz);
-        const __nv_bfloat16* src = vol + static_cast<uint32_t>(xv) * C + cvv * 8;
-        float v[8], g[8];
-        load8(src + base[0], v);
+        if (c >= ncell[cls]) continue;
+        const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
+        const __nv_bfloat16* src = vol + static_cast<uint32_t>(first[cls] + c) * C + cvv * 8;
+        const Corner c0 = cor[0], c1 = cor[1], c2 = cor[2], c3 = cor[3];
+        float v0[8], v1[8], v2[8], v3[8], g[8];
+        load8(src + c0.base, v0);
+        load8(src + c1.base, v1);
+        load8(src + c2.base, v2);
+        load8(src + c3.base, v3);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = v[j] * wyz[0];
-#pragma unroll
-        for (int k = 1; k < 4; ++k) {
-          load8(src + base[k], v);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = fmaf(v[j], wyz[k], g[j]);
-        }
-        float* dstt = s_tab + p.toff[li] + (d * cm + c) * C + cvv * 8;
+        for (int j = 0; j < 8; ++j) g[j] = fmaf(v3[j], c3.w, fmaf(v2[j], c2.w, fmaf(v1[j], c1.w, v0[j] * c0.w)));
+        float* dstt = tab + (d * cm + c) * C + cvv * 8;
         *reinterpret_cast<float4*>(dstt) = make_float4(g[0], g[1], g[2], g[3]);
         *reinterpret_cast<float4*>(dstt + 4) = make_float4(g[4], g[5], g[6], g[7]);
       }
@@ -505,45 +512,53 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         const int ch = rem - c * C;
         const int cls = shift_class(d);
         if (c >= s_ncell[li][cls]) continue;
-        const int xv = s_first[li][cls] + c;
-        uint32_t base[4];
-        float wyz[4];
-        tile_corners(t.qy, t.qz, d, p.R[li], static_cast<uint32_t>(C), base, wyz);
-        const __nv_bfloat16* src = vol + static_cast<uint32_t>(xv) * C + ch;
-        float r = __bfloat162float(src[base[0]]) * wyz[0];
+        const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
+        const __nv_bfloat16* src = vol + static_cast<uint32_t>(s_first[li][cls] + c) * C + ch;
+        float r = __bfloat162float(src[cor[0].base]) * cor[0].w;
 #pragma unroll
-        for (int k = 1; k < 4; ++k) r = fmaf(__bfloat162float(src[base[k]]), wyz[k], r);
+        for (int k = 1; k < 4; ++k) r = fmaf(__bfloat162float(src[cor[k].base]), cor[k].w, r);
         s_tab[p.toff[li] + (d * cm + c) * C + ch] = r;
       }
     }
   }
   __syncthreads();
 
-  // ---- phase L: vector columns ----
+  // ---- phase L: vector columns.  thread = (vector v, block of steps) ----
   const int nsteps = t.s_hi - t.s_lo;
   __nv_bfloat16* __restrict__ Xb = p.X + (t.g_tile0 + t.s_lo - p.tm.begin) * p.ldx;
   {
-    const float inv_nvec = 1.0f / static_cast<float>(p.nvec);
-    const int total = nsteps * p.nvec;
-    for (int it = tid; it < total; it += kRestThreads) {
-      const int sr = fast_div(it, inv_nvec);
-      const int v = it - sr * p.nvec;
-      const int s = t.s_lo + sr;
+    const int nblk = kRestThreads / p.nvec;              // step blocks (>= 2: nvec <= kMaxVec)
+    const int v = tid % p.nvec, blk = tid / p.nvec;
+    if (blk < nblk) {
+      const int per = (nsteps + nblk - 1) / nblk;
+      const int sr0 = blk * per, sr1 = min(nsteps, sr0 + per);
       const VecDesc vd = s_vec[v];
       const int li = vd.lc / 3, cls = vd.lc - li * 3;
-      const int c = s_rel[li][cls][s];
-      const float w1 = s_w1[li][cls][s];
-      const int c1 = min(c + 1, s_ncell[li][cls] - 1);
-      const float* g0p = s_tab + vd.tab + c * vd.cstride;
-      const float* g1p = s_tab + vd.tab + c1 * vd.cstride;
-      const float4 a0 = *reinterpret_cast<const float4*>(g0p), a1 = *reinterpret_cast<const float4*>(g0p + 4);
-      const float4 b0 = *reinterpret_cast<const float4*>(g1p), b1 = *reinterpret_cast<const float4*>(g1p + 4);
-      float out[8];
-      out[0] = fmaf(b0.x - a0.x, w1, a0.x); out[1] = fmaf(b0.y - a0.y, w1, a0.y);
-      out[2] = fmaf(b0.z - a0.z, w1, a0.z); out[3] = fmaf(b0.w - a0.w, w1, a0.w);
-      out[4] = fmaf(b1.x - a1.x, w1, a1.x); out[5] = fmaf(b1.y - a1.y, w1, a1.y);
-      out[6] = fmaf(b1.z - a1.z, w1, a1.z); out[7] = fmaf(b1.w - a1.w, w1, a1.w);
-      store8(Xb + static_cast<int64_t>(sr) * p.ldx + vd.col, out);
+      const int* __restrict__ rels = s_rel[li][cls] + t.s_lo;
+      const float* __restrict__ w1s = s_w1[li][cls] + t.s_lo;
+      const int last = s_ncell[li][cls] - 1;
+      const float* __restrict__ tab = s_tab + vd.tab;
+      float G0[8], Dv[8];
+      int cc = -1;
+      __nv_bfloat16* __restrict__ dst = Xb + static_cast<int64_t>(sr0) * p.ldx + vd.col;
+      for (int sr = sr0; sr < sr1; ++sr, dst += p.ldx) {
+        const int c = rels[sr];
+        if (c != cc) {
+          cc = c;
+          const float* g0p = tab + c * vd.cstride;
+          const float* g1p = tab + min(c + 1, last) * vd.cstride;
+          const float4 a0 = *reinterpret_cast<const float4*>(g0p), a1 = *reinterpret_cast<const float4*>(g0p + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(g1p), b1 = *reinterpret_cast<const float4*>(g1p + 4);
+          G0[0] = a0.x; G0[1] = a0.y; G0[2] = a0.z; G0[3] = a0.w; G0[4] = a1.x; G0[5] = a1.y; G0[6] = a1.z; G0[7] = a1.w;
+          Dv[0] = b0.x - a0.x; Dv[1] = b0.y - a0.y; Dv[2] = b0.z - a0.z; Dv[3] = b0.w - a0.w;
+          Dv[4] = b1.x - a1.x; Dv[5] = b1.y - a1.y; Dv[6] = b1.z - a1.z; Dv[7] = b1.w - a1.w;
+        }
+        const float w1 = w1s[sr];
+        float out[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = fmaf(Dv[j], w1, G0[j]);
+        store8(dst, out);
+      }
     }
   }
   // ---- tail: scalar levels, q, zero pad; one (step, 8-column group) item per thread ----
@@ -657,7 +672,12 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       r.R[nl] = ctx->vol_res[l];
       r.C[nl] = ctx->vol_ch[l];
       r.xoff[nl] = lay.vol_off[l] - shift;
-      if (vec) { r.nvec += LIST_NUM_DISP * (ctx->vol_ch[l] / 8); ++r.nvl; }
+      if (vec) {
+        const int ncv = ctx->vol_ch[l] / 8;
+        if (ncv & (ncv - 1)) return LIST_ENOSYS;       // hoist_rest_kernel decodes items with shifts
+        r.nvec += LIST_NUM_DISP * ncv;
+        ++r.nvl;
+      }
       else { if (lay.vol_off[l] < tail0) tail0 = lay.vol_off[l]; ++r.nsl; }
       ++nl;
     }
@@ -682,7 +702,12 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       floats += static_cast<size_t>(LIST_NUM_DISP) * cm * r.C[i];
       if (i < r.nvl) items += LIST_NUM_DISP * cm * (r.C[i] / 8);
     }
-    if (floats * 4 <= 96 * 1024 && floats < (1u << 24) && items < (1 << 20)) {
+    static const size_t budget = []() {                // LIST_B200_REST_SMEM_KB: table budget per CTA (tuning aid)
+      const char* e = getenv("LIST_B200_REST_SMEM_KB");
+      const long v = e ? atol(e) : 0;
+      return static_cast<size_t>(v >= 8 && v <= 200 ? v : 96) * 1024;
+    }();
+    if (floats * 4 <= budget && floats < (1u << 24) && items < (1 << 20)) {
       r.g_items = items;
       r.tm.kPz = kpz;
       *smem = floats * 4;
