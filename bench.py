@@ -229,7 +229,7 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # fused-kernel timing below
     roof_fused = None
     if fused:
         # the step IS one kernel launch (sdf_fused_kernel): time it alone
@@ -256,64 +256,75 @@ def main():
             hs = hotpath.HoistedState(ctx, kw)            # what list_sdf_grid builds at the start of every call
         except RuntimeError:
             hoisted = False
-    t_gather = t_mlp = 0.0
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_add = t_rest = t_mlp = 0.0
     for rep in range(2):                                   # rep 0 warms the allocator
-        tg = tm = 0.0
+        ta = tr = tm = 0.0
         for n0 in range(0, count, chunk):
             n = min(chunk, count - n0)
-            ev[0].record()
             if hoisted:
-                X = hs.gather_grid(0, res, begin + n0, n)
+                X = torch.empty(n, hs.k_h, device=dev, dtype=torch.bfloat16)
+                ev[0].record()
+                hs.gather_grid(0, res, begin + n0, n, parts=1, out=X)      # hoist_addend_kernel
+                ev[1].record()
+                hs.gather_grid(0, res, begin + n0, n, parts=2, out=X)      # hoist_rest_kernel
             else:
+                ev[0].record()
+                ev[1].record()
                 X = hotpath.gather_grid_features(ctx, 0, res, begin + n0, n)
-            ev[1].record()
-            hotpath.mlp(hs if hoisted else kw, X, SDF_SCALE)
             ev[2].record()
+            hotpath.mlp(hs if hoisted else kw, X, SDF_SCALE)
+            ev[3].record()
             torch.cuda.synchronize()
-            tg += ev[0].elapsed_time(ev[1])
-            tm += ev[1].elapsed_time(ev[2])
+            ta += ev[0].elapsed_time(ev[1])
+            tr += ev[1].elapsed_time(ev[2])
+            tm += ev[2].elapsed_time(ev[3])
             del X
-        t_gather, t_mlp = tg, tm
+        t_add, t_rest, t_mlp = ta, tr, tm
     if fused:
         os.environ.pop("LIST_B200_NO_FUSED", None)
     nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+    roofs = []
     if hoisted:
         # hoisted fc_0 (csrc/hoist.cu): the per-query GEMM runs on 512 addend + (k_out - hoist_cols) feature columns
         hoist_cols = lay.k_pad - (hs.k_h - 512)
         k_eff = 512 + lay.k_out - hoist_cols
         flop_exec = 2 * (k_eff * 512 + 512 * 256 + 256 * 256 + 256)
         hoisted_levels = [l for l in range(len(ctx.vols_cl)) if lay.vol_off[l] < hoist_cols and ctx.vol_ch[l] % 8 == 0]
-        read_bytes = (hs.buf.numel() - 512 * hs.k_h * 2
-                      + nbytes([v for l, v in enumerate(ctx.vols_cl) if l not in hoisted_levels]))
-        gather_bytes = count * k_eff * es + read_bytes
-        gather_kernel, mlp_note = "hoist_addend_kernel+hoist_rest_kernel", (
-            f"hoisted fc_0: {hoist_cols} of {lay.k_out} K columns (maps + levels {hoisted_levels}) are projected through W0 "
-            "once per image and sampled as one 512-wide addend block; `achieved` counts EXECUTED flops "
-            f"({flop_exec}/query), `effective` the reference's algorithmic {FLOP_PER_QUERY}/query")
+        proj_bytes = hs.buf.numel() - 512 * hs.k_h * 2                        # projected maps + coarse volumes
+        rest_vol_bytes = nbytes([v for l, v in enumerate(ctx.vols_cl) if l not in hoisted_levels])
+        mlp_note = (f"hoisted fc_0: {hoist_cols} of {lay.k_out} K columns (maps + levels {hoisted_levels}) are projected "
+                    "through W0 once per image and sampled as one 512-wide addend block; `achieved` counts EXECUTED flops "
+                    f"({flop_exec}/query), `effective` the reference's algorithmic {FLOP_PER_QUERY}/query")
+        gathers = [("hoist_addend_kernel", t_add, count * 512 * es + proj_bytes,
+                    "writes the 512 addend columns; reads the projected maps / coarse volumes once"),
+                   ("hoist_rest_kernel", t_rest, count * (k_eff - 512) * es + rest_vol_bytes,
+                    f"writes the remaining {k_eff - 512} feature columns; reads the fine volumes once")]
     else:
-        flop_exec = FLOP_PER_QUERY
-        gather_bytes = count * lay.k_out * es + nbytes([ctx.maps_cl, *ctx.vols_cl])   # SURVEY.md §8d (q generated in-kernel)
+        flop_exec, mlp_note = FLOP_PER_QUERY, None
         generic = os.environ.get("LIST_B200_GRID_GENERIC", "0") == "1"
-        gather_kernel, mlp_note = ("gather_fwd_kernel" if generic else "gather_grid_kernel"), None
+        gathers = [("gather_fwd_kernel" if generic else "gather_grid_kernel", t_rest,
+                    count * lay.k_out * es + nbytes([ctx.maps_cl, *ctx.vols_cl]),        # SURVEY.md §8d (q generated in-kernel)
+                    "writes the full 3610-column feature row")]
     mlp_tflops = flop_exec * count / (t_mlp * 1e-3) / 1e12
-    gather_gbs = gather_bytes / (t_gather * 1e-3) / 1e9
-    n_gather_kernels = 2 if hoisted else 1
     roof_mlp = {"kernel": "mlp_tc_kernel" if a.dtype == "bf16" else "sgemm_kernel", "bound": "tensor",
                 "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
-                "traffic": traffic.get("mlp"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
+                "traffic": traffic.get("mlp_tc_kernel"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
                 "flop_per_query": flop_exec, "effective": FLOP_PER_QUERY * count / (t_mlp * 1e-3) / 1e12,
                 "peak_source": pk["src"]}
     if mlp_note:
         roof_mlp["note"] = mlp_note
-    roof_gather = {"kernel": gather_kernel, "bound": "hbm",
-                   "achieved": gather_gbs, "peak": pk["hbm"],
-                   "unit": "GB/s", "frac": gather_gbs / pk["hbm"], "traffic": traffic.get("gather"),
-                   "ms_per_step": t_gather, "launches_per_step": n_chunks * n_gather_kernels,
-                   "bytes_per_step": gather_bytes, "peak_source": pk["src"]}
+    roofs.append(roof_mlp)
+    for name, tk, nb, what in gathers:
+        gbs = nb / (tk * 1e-3) / 1e9
+        roofs.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                      "frac": gbs / pk["hbm"], "traffic": traffic.get(name), "ms_per_step": tk,
+                      "launches_per_step": n_chunks, "bytes_per_step": nb, "what": what, "peak_source": pk["src"]})
+    roofs.sort(key=lambda r: -r["ms_per_step"])
     if fused:
-        dominant, other = roof_fused, {"unfused_pair_for_comparison": [roof_gather, roof_mlp]}
+        dominant, other = roof_fused, {"unfused_kernels_for_comparison": roofs}
     else:
-        dominant, other = (roof_mlp, roof_gather) if t_mlp >= t_gather else (roof_gather, roof_mlp)
+        dominant, other = roofs[0], roofs[1:]
 
     # ---- end to end through the C ABI with HOST buffers (H2D + prep + grid + D2H inside the timed region) ----
     e2e = None

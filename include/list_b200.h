@@ -177,13 +177,14 @@ LIST_API int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float*
  * the stages for tests and per-kernel timing.
  *   list_hoist_bytes            size of the caller-owned buffer holding W0h + projected tensors (0: not hoistable)
  *   list_hoist_prepare          projects every image of ctx and builds W0h; *w_hoisted = *w with w0 / k_pad replaced
- *   list_hoist_gather_grid_fwd  hoisted rows X[count][ldx >= k_h] for grid points [begin, begin+count) of `image` */
+ *   list_hoist_gather_grid_fwd  hoisted rows X[count][ldx >= k_h] for grid points [begin, begin+count) of `image`;
+ *                               parts: 1 = addend columns only, 2 = the remaining columns only, 3 = the whole row */
 LIST_API size_t list_hoist_bytes(const ListCtx* ctx, const ListWeights* w);
 LIST_API int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes,
                        ListWeights* w_hoisted, void* stream);
 LIST_API int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image,
                                int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count,
-                               void* X, int64_t ldx, void* stream);
+                               void* X, int64_t ldx, int32_t parts, void* stream);
 
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
  * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */

@@ -388,7 +388,8 @@ int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf
 }
 
 int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
-                               double bb_min, double bb_max, int64_t begin, int64_t count, void* X, int64_t ldx, void* stream) {
+                               double bb_min, double bb_max, int64_t begin, int64_t count, void* X, int64_t ldx, int32_t parts,
+                               void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   if ((rc = check_weights(w, -1))) return rc;
@@ -404,7 +405,8 @@ int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const v
                  (long long)begin, (long long)count);
   LIST_CHECK_ARG(hoist_buf && X && ldx >= pl.k_h && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
                  "list_hoist_gather_grid_fwd: hoist_buf/X NULL, X unaligned or ldx %lld < %d", (long long)ldx, pl.k_h);
-  return hoist::gather(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, X, ldx, static_cast<cudaStream_t>(stream));
+  LIST_CHECK_ARG(parts >= 1 && parts <= 3, "list_hoist_gather_grid_fwd: parts %d must be 1 (addend), 2 (rest) or 3 (both)", parts);
+  return hoist::gather(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, X, ldx, parts, static_cast<cudaStream_t>(stream));
 }
 
 int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw, int32_t B, int64_t N, float* sdf,
@@ -523,7 +525,7 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
         [&](int64_t i, void* X, cudaStream_t s) {
           int b; int64_t n0, n;
           span(i, b, n0, n);
-          return hoist::gather(ctx, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, s);
+          return hoist::gather(ctx, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, 3, s);
         },
         [&](int64_t i, void* X, cudaStream_t s) {
           int b; int64_t n0, n;

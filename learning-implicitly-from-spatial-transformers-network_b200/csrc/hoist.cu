@@ -561,15 +561,21 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       }
     }
   }
-  // ---- tail: scalar levels, q, zero pad; one (step, 8-column group) item per thread ----
+  // ---- tail: scalar levels, q, zero pad.  item = (step, 8-column group); groups beyond the q columns are zeros ----
   {
     const int ngrp = (p.k_h - p.tail0) >> 3;             // tail0 and k_h are multiples of 8
+    const int nlive = (nscal + 3 + 7) >> 3;              // groups holding scalar-level or q columns
     const float inv_ngrp = 1.0f / static_cast<float>(ngrp);
     const int total = nsteps * ngrp;
     for (int it = tid; it < total; it += kRestThreads) {
       const int sr = fast_div(it, inv_ngrp);
       const int gq = it - sr * ngrp;
       const int s = t.s_lo + sr;
+      __nv_bfloat16* drow = Xb + static_cast<int64_t>(sr) * p.ldx + p.tail0 + gq * 8;
+      if (gq >= nlive) {
+        *reinterpret_cast<uint4*>(drow) = make_uint4(0u, 0u, 0u, 0u);
+        continue;
+      }
       float out[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -589,7 +595,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         }
         out[j] = val;
       }
-      store8(Xb + static_cast<int64_t>(sr) * p.ldx + p.tail0 + gq * 8, out);
+      store8(drow, out);
     }
   }
 }
@@ -744,7 +750,7 @@ int check_gather(const ListCtx* ctx, const Plan& pl, int res) {
 
 // Feature rows X_h[count][ldx] of grid points [begin, begin+count) of image `image`.
 int gather(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max,
-           int64_t begin, int64_t count, void* X, int64_t ldx, cudaStream_t st) {
+           int64_t begin, int64_t count, void* X, int64_t ldx, int parts, cudaStream_t st) {
   if (count == 0) return LIST_OK;
   ListLayout lay;
   const int rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr);
@@ -775,12 +781,16 @@ int gather(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int r
   fill_tilemap(&r.tm, res, bb_min, bb_max, begin, count, r.tm.kPz);
 
   static const int vec = []() { const char* e = getenv("LIST_B200_HOIST_VEC"); return (e && e[0] == '8') ? 8 : 4; }();
-  if (vec == 8) hoist_addend_kernel<8><<<tile_count(a.tm), kN0 / 8, 0, st>>>(a);
-  else hoist_addend_kernel<4><<<tile_count(a.tm), kN0 / 4, 0, st>>>(a);
-  LIST_LAUNCH_CHECK("hoist_addend_kernel");
-  LIST_CUDA(cudaFuncSetAttribute(hoist_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  hoist_rest_kernel<<<tile_count(r.tm), kRestThreads, smem, st>>>(r);
-  LIST_LAUNCH_CHECK("hoist_rest_kernel");
+  if (parts & kPartAddend) {
+    if (vec == 8) hoist_addend_kernel<8><<<tile_count(a.tm), kN0 / 8, 0, st>>>(a);
+    else hoist_addend_kernel<4><<<tile_count(a.tm), kN0 / 4, 0, st>>>(a);
+    LIST_LAUNCH_CHECK("hoist_addend_kernel");
+  }
+  if (parts & kPartRest) {
+    LIST_CUDA(cudaFuncSetAttribute(hoist_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    hoist_rest_kernel<<<tile_count(r.tm), kRestThreads, smem, st>>>(r);
+    LIST_LAUNCH_CHECK("hoist_rest_kernel");
+  }
   return LIST_OK;
 }
 

@@ -266,13 +266,15 @@ class HoistedState:
         n0 = self.base.w0.shape[0]
         return self.buf[: n0 * self.k_h * 2].view(torch.bfloat16).view(n0, self.k_h)
 
-    def gather_grid(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5):
+    def gather_grid(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5,
+                    parts: int = 3, out: Optional[torch.Tensor] = None):
+        """Hoisted feature rows; parts: 1 = addend columns only, 2 = remaining columns only, 3 = whole row."""
         dev = self.buf.device
-        X = torch.empty(count, self.k_h, device=dev, dtype=torch.bfloat16)
+        X = out if out is not None else torch.empty(count, self.k_h, device=dev, dtype=torch.bfloat16)
         cs, ws = self.ctx.struct(), self.base.struct()
         with torch.cuda.device(dev):
             _C.check(_C.lib().list_hoist_gather_grid_fwd(C.byref(cs), C.byref(ws), self.buf.data_ptr(), image, res, bb_min,
-                                                         bb_max, begin, count, X.data_ptr(), self.k_h, _stream()),
+                                                         bb_max, begin, count, X.data_ptr(), self.k_h, parts, _stream()),
                      "list_hoist_gather_grid_fwd")
         return X
 
