@@ -172,19 +172,24 @@ LIST_API int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float*
 /* Hoisted fc_0 for dense grids in bf16 mode (csrc/hoist.cu).  fc_0 (reference modules.py:197,276) and the
  * samplers in front of it (modules.py:48-52, 264-265) are linear, so the maps and the coarse voxel levels
  * (R <= 16) are projected through their column blocks of W0 once per image and sampled per query as ONE
- * 512-wide addend block; the feature row shrinks from 3648 to 1344 columns and W0 to
- * W0h = [I_512 | remaining columns].  list_sdf_grid does all of this internally; the three calls below expose
- * the stages for tests and per-kernel timing.
- *   list_hoist_bytes            size of the caller-owned buffer holding W0h + projected tensors (0: not hoistable)
- *   list_hoist_prepare          projects every image of ctx and builds W0h; *w_hoisted = *w with w0 / k_pad replaced
+ * 512-wide addend block (which also carries the bias b0); the feature row shrinks from 3648 to
+ * [addend 512 | remaining k_pad - hoist_cols columns] and fc_0 runs on the remaining columns only, the addend
+ * being added to its accumulator in the epilogue.  list_sdf_grid does all of this internally; the calls below
+ * expose the stages for tests and per-kernel timing.
+ *   list_hoist_layout           hoist_cols (leading columns of the full row that are hoisted) and k_h (row width)
+ *   list_hoist_bytes            size of the caller-owned buffer holding the projected tensors (0: not hoistable)
+ *   list_hoist_prepare          projects every image of ctx
  *   list_hoist_gather_grid_fwd  hoisted rows X[count][ldx >= k_h] for grid points [begin, begin+count) of `image`;
- *                               parts: 1 = addend columns only, 2 = the remaining columns only, 3 = the whole row */
+ *                               parts: 1 = addend columns only, 2 = the remaining columns only, 3 = the whole row
+ *   list_mlp_hoisted_fwd        a-6 on hoisted rows (w = the ORIGINAL weights) */
+LIST_API int list_hoist_layout(const ListCtx* ctx, const ListWeights* w, int32_t* hoist_cols, int32_t* k_h);
 LIST_API size_t list_hoist_bytes(const ListCtx* ctx, const ListWeights* w);
-LIST_API int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes,
-                       ListWeights* w_hoisted, void* stream);
+LIST_API int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, void* stream);
 LIST_API int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image,
                                int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count,
                                void* X, int64_t ldx, int32_t parts, void* stream);
+LIST_API int list_mlp_hoisted_fwd(const ListWeights* w, int32_t hoist_cols, const void* Xh, int64_t ldx, int64_t rows,
+                         float* sdf, float out_div, void* stream);
 
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
  * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */

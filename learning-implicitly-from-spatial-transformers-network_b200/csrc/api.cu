@@ -43,6 +43,8 @@ int gather_bwd(const ListCtx* ctx, const float* q, int q_is_raw, int B, int64_t 
                const ListGrads* g, cudaStream_t st);
 int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
                float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
+int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
+                       float out_div, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
 int sdf_grid_fused(const ListCtx* ctx, const ListWeights* w, int image, int res, double bb_min, double bb_max,
                    int64_t begin, int64_t count, float* sdf, float out_div, cudaStream_t st);
 
@@ -364,8 +366,21 @@ size_t list_hoist_bytes(const ListCtx* ctx, const ListWeights* w) {
   return pl.total;
 }
 
-int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, ListWeights* w_hoisted,
-                       void* stream) {
+int list_hoist_layout(const ListCtx* ctx, const ListWeights* w, int32_t* hoist_cols, int32_t* k_h) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if ((rc = check_weights(w, -1))) return rc;
+  hoist::Plan pl;
+  if (hoist::make_plan(ctx, w, &pl) != LIST_OK) {
+    set_error("list_hoist_layout: this configuration has no hoisted path (bf16, fc_0 width 512, coarse levels with C %% 64 == 0)");
+    return LIST_ENOSYS;
+  }
+  if (hoist_cols) *hoist_cols = pl.hoist_cols;
+  if (k_h) *k_h = pl.k_h;
+  return LIST_OK;
+}
+
+int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   if ((rc = check_weights(w, -1))) return rc;
@@ -378,13 +393,21 @@ int list_hoist_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf
     set_error("list_hoist_prepare: hoist_buf NULL, not 256B aligned or %zu B < required %zu B", hoist_bytes, pl.total);
     return LIST_ENOMEM;
   }
-  if ((rc = hoist::prepare(ctx, w, pl, hoist_buf, static_cast<cudaStream_t>(stream)))) return rc;
-  if (w_hoisted) {
-    *w_hoisted = *w;
-    w_hoisted->w0 = static_cast<char*>(hoist_buf) + pl.off_w0h;
-    w_hoisted->k_pad = pl.k_h;
-  }
-  return LIST_OK;
+  return hoist::prepare(ctx, w, pl, hoist_buf, static_cast<cudaStream_t>(stream));
+}
+
+int list_mlp_hoisted_fwd(const ListWeights* w, int32_t hoist_cols, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
+                         float out_div, void* stream) {
+  int rc = check_weights(w, -1);
+  if (rc) return rc;
+  LIST_CHECK_ARG(w->dtype == LIST_BF16, "list_mlp_hoisted_fwd: bf16 tensor-core kernel only");
+  LIST_CHECK_ARG(rows >= 0, "list_mlp_hoisted_fwd: rows < 0");
+  if (rows == 0) return LIST_OK;
+  LIST_CHECK_ARG(Xh && sdf && out_div != 0.f, "list_mlp_hoisted_fwd: X/sdf NULL or out_div == 0");
+  LIST_CHECK_ARG(hoist_cols > 0 && hoist_cols < w->k_pad && hoist_cols % 64 == 0, "list_mlp_hoisted_fwd: hoist_cols %d invalid for k_pad %d",
+                 hoist_cols, w->k_pad);
+  return mlp_tc_fwd_hoisted(w, hoist_cols, w->k_pad - hoist_cols, Xh, ldx, rows, sdf, out_div, nullptr, nullptr, nullptr,
+                            static_cast<cudaStream_t>(stream));
 }
 
 int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
@@ -406,7 +429,7 @@ int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const v
   LIST_CHECK_ARG(hoist_buf && X && ldx >= pl.k_h && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0,
                  "list_hoist_gather_grid_fwd: hoist_buf/X NULL, X unaligned or ldx %lld < %d", (long long)ldx, pl.k_h);
   LIST_CHECK_ARG(parts >= 1 && parts <= 3, "list_hoist_gather_grid_fwd: parts %d must be 1 (addend), 2 (rest) or 3 (both)", parts);
-  return hoist::gather(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, X, ldx, parts, static_cast<cudaStream_t>(stream));
+  return hoist::gather(ctx, w, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, X, ldx, parts, static_cast<cudaStream_t>(stream));
 }
 
 int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32_t q_is_raw, int32_t B, int64_t N, float* sdf,
@@ -512,25 +535,24 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
     n = (count - n0 < chunk_rows) ? (count - n0) : chunk_rows;
   };
   // bf16: hoisted fc_0 (hoist.cu) -- project maps / coarse levels through their W0 blocks once per call, then the
-  // per-chunk gather writes the 1344-column hoisted row and the MLP runs on W0h.
+  // per-chunk gather writes the hoisted row [addend 512 | 832 columns]; fc_0 runs on the 832 columns and adds the addend
+  // block in its epilogue.
   hoist::Plan pl;
   if (two && hoist_enabled() && hoist::make_plan(ctx, w, &pl) == LIST_OK && hoist::check_gather(ctx, pl, res) == LIST_OK) {
     void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
     if ((rc = hoist::prepare(ctx, w, pl, hbuf, st))) return rc;
-    ListWeights wh = *w;
-    wh.w0 = static_cast<char*>(hbuf) + pl.off_w0h;
-    wh.k_pad = pl.k_h;
     return run_chunks(
         per_image * ctx->B, xbuf, overlap_enabled(), st,
         [&](int64_t i, void* X, cudaStream_t s) {
           int b; int64_t n0, n;
           span(i, b, n0, n);
-          return hoist::gather(ctx, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, 3, s);
+          return hoist::gather(ctx, w, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, 3, s);
         },
         [&](int64_t i, void* X, cudaStream_t s) {
           int b; int64_t n0, n;
           span(i, b, n0, n);
-          return list_mlp_fwd(&wh, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, nullptr, 0, s);
+          return mlp_tc_fwd_hoisted(w, pl.hoist_cols, pl.k_h - 512, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0,
+                                    sdf_scale, nullptr, nullptr, nullptr, s);
         });
   }
   return run_chunks(
@@ -570,8 +592,8 @@ static void plan_host(const int32_t* map_ch, const int32_t* map_in, int n_maps, 
   size_t ws = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(dtype), 256);
   if (dtype == LIST_BF16) {
     ws *= 2;                                           // double-buffered feature rows (run_chunks)
-    // hoisted-fc_0 tensors (hoist.cu): W0h + projected maps + 7 projected copies of every level with R <= 16
-    size_t h = align_up(static_cast<size_t>(512) * lay.k_pad * 2, 256) + align_up(static_cast<size_t>(B) * S * S * 512 * 2, 256);
+    // hoisted-fc_0 tensors (hoist.cu): projected maps + 7 projected copies of every level with R <= 16
+    size_t h = align_up(static_cast<size_t>(B) * S * S * 512 * 2, 256);
     for (int l = 0; l < n_levels; ++l)
       if (vol_res[l] <= 16) h += align_up(static_cast<size_t>(7) * B * vol_res[l] * vol_res[l] * vol_res[l] * 512 * 2, 256);
     ws += h + 256;

@@ -8,14 +8,13 @@
 // projecting f through its block of W0 ONCE per image (a small tensor-core GEMM over pixels / voxels,
 // mlp_tc_project) and sampling the projected tensor per query.  On a dense grid this removes
 //        1024 (maps) + 7*128 (level 16^3) + 7*128 (level 8^3) = 2816 of the 3610 K columns
-// from the per-query GEMM and replaces them by ONE 512-wide "addend" block whose weight block is the
-// identity: the feature row shrinks from 3648 to 512 + 832 = 1344 columns,
+// from the per-query GEMM and replaces them by ONE 512-wide "addend" block (which also carries the bias b0) that
+// the MLP kernel adds to fc_0's accumulator in its epilogue: the feature row shrinks from 3648 to 512 + 832 columns,
 //        X_h = [ addend(512) | level 32^3 (448) | level 64^3 (224) | level 128^3 (112) | occupancy (7) | q (3) | 0-pad ]
-//        W0h = [ I_512       | the same columns of W0 ............................................................ ]
-// so that  W0h · X_h == W0 · X  exactly in real arithmetic.  The fp32 parity path is untouched.
+// and fc_0 runs on K = 832 with the matching columns of W0:  relu(W0[:, 2816:] · X_h[512:] + addend) == relu(W0 · X + b0)
+// in real arithmetic.  The fp32 parity path is untouched.
 //
 // Kernels here:
-//   build_w0h_kernel     W0h from W0 (identity block + verbatim tail columns).
 //   hoist_addend_kernel  per 64-point tile of the grid, 64 threads, thread = 8 of the 512 addend channels:
 //                        walks the z-run with the separable scheme of gather_grid.cu -- bilinear taps of the
 //                        projected map (cell cache) + for each hoisted level the three W-shift classes
@@ -87,6 +86,7 @@ struct AddParams {
   const __nv_bfloat16* pvol[kMaxH]; // image's slab of displacement 0: [R][R][R][512]
   uint32_t dstride[kMaxH];          // elements between displacement slabs
   const float* T;
+  const float* b0;                  // fc_0 bias, folded into the addend
   __nv_bfloat16* X;
   int64_t ldx;
   int S, nh;
@@ -126,18 +126,6 @@ __device__ __forceinline__ void tile_corners(float qy, float qz, int d, int R, u
     const int tz = k >> 1, ty = k & 1;
     base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * row_elems;
     wyz[k] = wy[ty] * wz[tz];
-  }
-}
-
-// ------------------------------------------------------------------ W0h
-__global__ void build_w0h_kernel(const __nv_bfloat16* __restrict__ w0, int k_pad, int hoist_cols, int k_h,
-                                 __nv_bfloat16* __restrict__ w0h) {
-  const int n = blockIdx.x;
-  for (int j = threadIdx.x; j < k_h; j += blockDim.x) {
-    __nv_bfloat16 v;
-    if (j < kN0) v = __float2bfloat16_rn(j == n ? 1.0f : 0.0f);
-    else v = w0[static_cast<size_t>(n) * k_pad + hoist_cols + (j - kN0)];
-    w0h[static_cast<size_t>(n) * k_h + j] = v;
   }
 }
 
@@ -190,8 +178,12 @@ __device__ __forceinline__ void load_column(const __nv_bfloat16* __restrict__ pv
 
 // Control word of a step: bits 0-5 = class c (level c/3, W-shift class c%3) enters a new voxel cell,
 // bit 6 = the 2-D sample enters a new pixel cell, bits 8-15 = steps until the next step with any of those bits.
+#ifndef LIST_ADDEND_MINBLOCKS
+#define LIST_ADDEND_MINBLOCKS 4        // <= 128 registers.  Measured at 256^3 (same box): 172 regs (uncapped) 21.7 ms, 128 regs 17.1 ms,
+                                       // 96 regs 18.4 ms alone; pipelined with the MLP 48.5 / 42.7 / 46.8 ms per grid
+#endif
 template <int V>
-__global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p) {
+__global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_kernel(const AddParams p) {
   constexpr int NT = kN0 / V;
   constexpr int NC = kMaxH * 3;
   __shared__ __align__(16) float s_w[kTile][12];        // per step: w0 of the 6 classes, w00 w01 w10 w11, 2 pad
@@ -285,7 +277,7 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
 
   const int cv = tid;
   float G1[NC][V], D[NC][V], gsum[V];
-  float v00[V], v01[V], v10[V], v11[V];
+  float v00[V], v01[V], v10[V], v11[V], bias[V];
   int cur[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -294,7 +286,7 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
     for (int j = 0; j < V; ++j) { G1[c][j] = 0.f; D[c][j] = 0.f; }
   }
 #pragma unroll
-  for (int j = 0; j < V; ++j) { v00[j] = v01[j] = v10[j] = v11[j] = 0.f; gsum[j] = 0.f; }
+  for (int j = 0; j < V; ++j) { v00[j] = v01[j] = v10[j] = v11[j] = 0.f; bias[j] = __ldg(p.b0 + cv * V + j); gsum[j] = bias[j]; }
 
   __nv_bfloat16* __restrict__ dst = p.X + (t.g_tile0 + t.s_lo - p.tm.begin) * p.ldx + cv * V;
   const int lim = p.S - 1;
@@ -337,9 +329,9 @@ __global__ void __launch_bounds__(kN0 / V) hoist_addend_kernel(const AddParams p
       }
 #pragma unroll
       for (int j = 0; j < V; ++j) {
-        float a = G1[0][j];
+        float a = bias[j];
 #pragma unroll
-        for (int c = 1; c < NC; ++c) a += G1[c][j];
+        for (int c = 0; c < NC; ++c) a += G1[c][j];
         gsum[j] = a;
       }
     }
@@ -623,7 +615,6 @@ int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl) {
   pl->k_h = kN0 + (lay.k_pad - cols);
   auto up = [](size_t x) { return (x + 255) / 256 * 256; };
   size_t off = 0;
-  pl->off_w0h = off; off += up(static_cast<size_t>(kN0) * pl->k_h * 2);
   pl->off_pmap = off; off += up(static_cast<size_t>(ctx->B) * ctx->map_size * ctx->map_size * kN0 * 2);
   for (int h = 0; h < pl->nh; ++h) {
     const size_t R = ctx->vol_res[pl->lev[h]];
@@ -635,15 +626,12 @@ int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl) {
   return LIST_OK;
 }
 
-// Projects the maps and the hoisted levels of every image through their W0 blocks and builds W0h.
+// Projects the maps and the hoisted levels of every image through their W0 blocks.
 int prepare(const ListCtx* ctx, const ListWeights* w, const Plan& pl, void* buf, cudaStream_t st) {
   char* base = static_cast<char*>(buf);
   ListLayout lay;
   int rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr);
   if (rc) return rc;
-  build_w0h_kernel<<<kN0, 256, 0, st>>>(static_cast<const __nv_bfloat16*>(w->w0), w->k_pad, pl.hoist_cols, pl.k_h,
-                                        reinterpret_cast<__nv_bfloat16*>(base + pl.off_w0h));
-  LIST_LAUNCH_CHECK("build_w0h_kernel");
   const int64_t px = static_cast<int64_t>(ctx->B) * ctx->map_size * ctx->map_size;
   if ((rc = mlp_tc_project(w, lay.map_off, 0, 1, ctx->map_channels, ctx->maps, ctx->map_channels, px, base + pl.off_pmap, st)))
     return rc;
@@ -749,7 +737,7 @@ int check_gather(const ListCtx* ctx, const Plan& pl, int res) {
 }
 
 // Feature rows X_h[count][ldx] of grid points [begin, begin+count) of image `image`.
-int gather(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max,
+int gather(const ListCtx* ctx, const ListWeights* w, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max,
            int64_t begin, int64_t count, void* X, int64_t ldx, int parts, cudaStream_t st) {
   if (count == 0) return LIST_OK;
   ListLayout lay;
@@ -767,6 +755,7 @@ int gather(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int r
   }
   for (int h = pl.nh; h < kMaxH; ++h) { a.pvol[h] = a.pvol[0]; a.dstride[h] = 0; a.R[h] = 1; }
   a.T = ctx->trans_mat + image * 12;
+  a.b0 = w->b0;
   a.X = static_cast<__nv_bfloat16*>(X);
   a.ldx = ldx;
   a.S = ctx->map_size;

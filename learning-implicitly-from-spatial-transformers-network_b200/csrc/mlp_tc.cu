@@ -53,7 +53,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ sdf,
               long long rows, int nk0, float out_div, float* __restrict__ dbg1, float* __restrict__ dbg2,
               float* __restrict__ dbg3, __nv_bfloat16* __restrict__ proj_out, int proj_groups, int proj_w_col_stride,
-              long long proj_out_group_stride) {
+              long long proj_out_group_stride, const __nv_bfloat16* __restrict__ addend, long long ld_add) {
   using C = Cfg<CG, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -221,6 +221,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       const int group = tile / tiles_per_group;
       const long long row = (tile - group * tiles_per_group) * rows_per_tile + rank * BM + quarter * 32 + lane;
       // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
+      if (addend != nullptr) {                               // the epilogue is idle while fc_0 runs: pull the row's addend into L2
+        const __nv_bfloat16* const arow = addend + (row < rows ? row : rows - 1) * ld_add;
+#pragma unroll
+        for (int i = 0; i < (N0 * 2) / 128; ++i)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(arow) + i * 128));
+      }
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (proj) {                                           // raw accumulator -> bf16 row of the group's slab
@@ -246,6 +252,51 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
         continue;
       }
+      if (addend != nullptr) {
+        // Hoisted rows (hoist.cu): fc_0's accumulator covers only the non-hoisted K columns; the 512-wide addend
+        // block of the row (projected maps / coarse levels + bias b0, bf16) is added here.  The row was prefetched
+        // into L2 before the dfull wait; two 32-column chunks are kept in flight in registers.
+        const __nv_bfloat16* const arow = addend + (row < rows ? row : rows - 1) * ld_add;
+#ifndef LIST_MLP_ADD_DEPTH
+#define LIST_MLP_ADD_DEPTH 2
+#endif
+        constexpr int kDepth = LIST_MLP_ADD_DEPTH;          // 32-column chunks of the addend kept in flight
+        uint4 pq[kDepth][4];
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pq[d][i] = __ldg(reinterpret_cast<const uint4*>(arow + d * 32) + i);
+        auto chunk = [&](int j, uint4 (&pq)[4]) {
+          uint32_t v[32], u[16];
+          tmem_ld32(tq + j * 32, v);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t w4[4] = {pq[i].x, pq[i].y, pq[i].z, pq[i].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[8 * i + 2 * e] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e]) + __uint_as_float(w4[e] << 16), 0.f));
+              v[8 * i + 2 * e + 1] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e + 1]) + __uint_as_float(w4[e] & 0xffff0000u), 0.f));
+            }
+          }
+          if (j + kDepth < N0 / 32) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) pq[i] = __ldg(reinterpret_cast<const uint4*>(arow + (j + kDepth) * 32) + i);
+          }
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          tmem_st16(tq + j * 16, u);
+          if (dbg1 != nullptr && row < rows) {
+            float* const drow = dbg1 + row * N0 + j * 32;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) drow[i] = __uint_as_float(v[i]);
+          }
+        };
+#pragma unroll 1
+        for (int j = 0; j < N0 / 32; j += kDepth) {
+#pragma unroll
+          for (int d = 0; d < kDepth; ++d) chunk(j + d, pq[d]);
+        }
+      } else {
 #pragma unroll 1
       for (int j = 0; j < N0 / 32; ++j) {
         uint32_t v[32], u[16];
@@ -262,6 +313,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           for (int i = 0; i < 32; ++i)
             dbg1[row * N0 + j * 32 + i] = fmaxf(__uint_as_float(v[i]) + s_b0[j * 32 + i], 0.f);
         }
+      }
       }
       tmem_wait_st();
       tc_fence_before();
@@ -325,6 +377,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 }
 
 // ------------------------------------------------------------------ host side
+struct AddArgs {                        // hoisted rows: fc_0 over k columns of X only, addend block added in the epilogue
+  const __nv_bfloat16* addend = nullptr;
+  int64_t ld = 0;
+  int k = 0;                            // K of fc_0 (columns of X / of the W0 view); 0 = w->k_pad
+};
 struct ProjArgs {                       // projection mode (see the kernel); all zero = the full MLP
   __nv_bfloat16* out = nullptr;         // [groups][rows][512]
   int groups = 1;
@@ -334,13 +391,13 @@ struct ProjArgs {                       // projection mode (see the kernel); all
 
 template <int CG, int ST>
 static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div,
-                  float* dbg1, float* dbg2, float* dbg3, const ProjArgs& pa, cudaStream_t st) {
+                  float* dbg1, float* dbg2, float* dbg3, const ProjArgs& pa, const AddArgs& aa, cudaStream_t st) {
   using C = Cfg<CG, ST>;
   CUtensorMap tmX, tmW0, tmW1, tmW2;
   int rc;
   const bool proj = pa.out != nullptr;
-  const int k0 = proj ? pa.k : w->k_pad;
-  const uint64_t w0_cols = proj ? static_cast<uint64_t>(pa.w_col_stride) * (pa.groups - 1) + pa.k : w->k_pad;
+  const int k0 = proj ? pa.k : (aa.k > 0 ? aa.k : w->k_pad);
+  const uint64_t w0_cols = proj ? static_cast<uint64_t>(pa.w_col_stride) * (pa.groups - 1) + pa.k : k0;
   if ((rc = make_map_bf16(&tmX, X, k0, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx)))) return rc;
   if ((rc = make_map_bf16(&tmW0, w->w0, w0_cols, N0, w->k_pad))) return rc;
   if ((rc = make_map_bf16(&tmW1, w->w1, N0, N1, N0))) return rc;
@@ -367,7 +424,7 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   const int nk0 = k0 / BK;
   LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG, ST>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
                                sdf, static_cast<long long>(rows), nk0, out_div, dbg1, dbg2, dbg3, pa.out, pa.groups,
-                               pa.w_col_stride, static_cast<long long>(rows) * N0));
+                               pa.w_col_stride, static_cast<long long>(rows) * N0, aa.addend, static_cast<long long>(aa.ld)));
   return LIST_OK;
 }
 
@@ -384,11 +441,35 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
   LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(X) & 15) == 0, "mlp_tc: X must be 16-byte aligned");
   LIST_CHECK_ARG(rows < (1LL << 31), "mlp_tc: rows %lld too large for one call", (long long)rows);
   const tc::ProjArgs none;
-  if (variant == 1) return tc::launch<1, 2>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, st);
+  const tc::AddArgs noadd;
+  if (variant == 1) return tc::launch<1, 2>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, noadd, st);
   // variant 2 = CTA pair with a 4-stage operand ring (192 KB); variant 3 = the same with 3 stages (144 KB),
   // which leaves shared memory for gather CTAs of the next chunk to co-reside on the SM (api.cu pipeline).
-  if (variant == 3) return tc::launch<2, 3>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, st);
-  return tc::launch<2, 4>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, st);
+  if (variant == 3) return tc::launch<2, 3>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, noadd, st);
+  return tc::launch<2, 4>(w, X, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, noadd, st);
+}
+
+// Hoisted rows (hoist.cu): Xh[rows][ldx] = [addend n0 (incl. bias b0) | k columns]; fc_0 runs on W0[:, col0 : col0 + k]
+// only and the addend block is added to its accumulator in the epilogue; fc_1, fc_2, fc_out as in mlp_tc_fwd.
+int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
+                       float out_div, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
+  if (rows == 0) return LIST_OK;
+  LIST_CHECK_ARG(w->n0 == tc::N0 && w->n1 == tc::N1 && w->n2 == tc::N2,
+                 "mlp_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
+  LIST_CHECK_ARG(k > 0 && k % tc::BK == 0 && col0 % 8 == 0 && col0 + k <= w->k_pad, "mlp_tc hoisted: W0 columns [%d, +%d) invalid for k_pad %d",
+                 col0, k, w->k_pad);
+  LIST_CHECK_ARG(ldx % 8 == 0 && ldx >= tc::N0 + k, "mlp_tc hoisted: ldx %lld must be >= %d and a multiple of 8", (long long)ldx, tc::N0 + k);
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(Xh) & 15) == 0, "mlp_tc hoisted: X must be 16-byte aligned");
+  LIST_CHECK_ARG(rows < (1LL << 31), "mlp_tc hoisted: rows %lld too large for one call", (long long)rows);
+  ListWeights wv = *w;
+  wv.w0 = static_cast<const __nv_bfloat16*>(w->w0) + col0;
+  const __nv_bfloat16* xh = static_cast<const __nv_bfloat16*>(Xh);
+  tc::AddArgs aa;
+  aa.addend = xh;
+  aa.ld = ldx;
+  aa.k = k;
+  const tc::ProjArgs none;
+  return tc::launch<2, 4>(&wv, xh + tc::N0, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, aa, st);
 }
 
 // Projection through fc_0 only (hoist.cu): out[g][r][0..512) = sum_k X[r][k] * W0[n][col0 + g*col_stride + k],
@@ -412,7 +493,7 @@ int mlp_tc_project(const ListWeights* w, int col0, int col_stride, int groups, i
   pa.groups = groups;
   pa.w_col_stride = col_stride;
   pa.k = k;
-  return tc::launch<2, 4>(&wv, X, ldx, rows, nullptr, 1.0f, nullptr, nullptr, nullptr, pa, st);
+  return tc::launch<2, 4>(&wv, X, ldx, rows, nullptr, 1.0f, nullptr, nullptr, nullptr, pa, tc::AddArgs{}, st);
 }
 
 }  // namespace list

@@ -238,8 +238,8 @@ def gather_grid_features(ctx: HotPathContext, image: int, res: int, begin: int, 
 
 # ------------------------------------------------------------------------------ hoisted fc_0 (dense grids, bf16)
 class HoistedState:
-    """Output of list_hoist_prepare: the caller-owned buffer with W0h and the projected maps / coarse levels
-    (csrc/hoist.cu), plus the ListWeights view whose w0 is W0h.  Quacks like KernelWeights for `mlp`."""
+    """Output of list_hoist_prepare: the caller-owned buffer with the projected maps / coarse levels
+    (csrc/hoist.cu) of every image of `ctx`, for `weights`."""
 
     def __init__(self, ctx: HotPathContext, weights: KernelWeights):
         dev = _require_cuda(ctx.maps_cl, weights.w0)
@@ -249,22 +249,26 @@ class HoistedState:
         need = lib.list_hoist_bytes(C.byref(cs), C.byref(ws))
         if need == 0:
             raise RuntimeError("list_hoist_bytes returned 0: this configuration has no hoisted path")
+        hc, kh = C.c_int32(0), C.c_int32(0)
+        _C.check(lib.list_hoist_layout(C.byref(cs), C.byref(ws), C.byref(hc), C.byref(kh)), "list_hoist_layout")
+        self.hoist_cols, self.k_h = hc.value, kh.value
         self.buf = torch.empty(need, device=dev, dtype=torch.uint8)
-        self._w = _C.ListWeights()
         with torch.cuda.device(dev):
-            _C.check(lib.list_hoist_prepare(C.byref(cs), C.byref(ws), self.buf.data_ptr(), need, C.byref(self._w), _stream()),
+            _C.check(lib.list_hoist_prepare(C.byref(cs), C.byref(ws), self.buf.data_ptr(), need, _stream()),
                      "list_hoist_prepare")
-        self.k_h = self._w.k_pad
-        self.dtype = weights.dtype
-        self.w0 = self.buf                      # device check in mlp()
 
-    def struct(self) -> _C.ListWeights:
-        return self._w
-
-    def w0h(self) -> torch.Tensor:
-        """W0h as a (512, k_h) bf16 tensor (a view of the buffer)."""
-        n0 = self.base.w0.shape[0]
-        return self.buf[: n0 * self.k_h * 2].view(torch.bfloat16).view(n0, self.k_h)
+    def mlp(self, X: torch.Tensor, out_div: float = 1.0) -> torch.Tensor:
+        """Row a-6 on hoisted rows X (rows, k_h) = [addend 512 | remaining columns]."""
+        dev = _require_cuda(X, self.base.w0)
+        if X.dtype != torch.bfloat16 or X.shape[1] < self.k_h or X.stride(1) != 1:
+            raise ValueError("hoisted rows must be bf16 with at least k_h contiguous columns")
+        rows = X.shape[0]
+        sdf = torch.empty(rows, device=dev, dtype=torch.float32)
+        ws = self.base.struct()
+        with torch.cuda.device(dev):
+            _C.check(_C.lib().list_mlp_hoisted_fwd(C.byref(ws), self.hoist_cols, X.data_ptr(), X.stride(0), rows,
+                                                   sdf.data_ptr(), float(out_div), _stream()), "list_mlp_hoisted_fwd")
+        return sdf
 
     def gather_grid(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5,
                     parts: int = 3, out: Optional[torch.Tensor] = None):

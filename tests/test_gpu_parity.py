@@ -306,28 +306,40 @@ def test_backward_vs_reference_golden():
 # ------------------------------------------------------------------ hoisted fc_0 (dense grids, bf16)
 def test_hoisted_rows_addend_and_verbatim_columns():
     """csrc/hoist.cu: the hoisted row is [addend(512) | the non-hoisted columns of the full row verbatim];
-    the addend equals W0[:, :hoist_cols] applied to the hoisted columns of the full (walker) row."""
+    the addend equals W0[:, :hoist_cols] applied to the hoisted columns of the full (walker) row, plus b0;
+    the hoisted MLP (fc_0 on the remaining columns + addend in its epilogue) equals the MLP on full rows."""
     inp = synth.make_inputs(seed=21, B=2, N=8, size="small", trans="camera")
     g = inp.to(DEV)
     ctx, kw = ctx_and_weights(g, "bf16")
     ctx32, kw32 = ctx_and_weights(g, "fp32")
     hs = hotpath.HoistedState(ctx, kw)
     lay = ctx.layout
-    hoist_cols = lay.k_pad - (hs.k_h - 512)
-    w0h = hs.w0h().float()
-    assert torch.equal(w0h[:, :512], torch.eye(512, device=DEV))
-    assert torch.equal(w0h[:, 512:], kw.w0[:, hoist_cols:].float())
+    hoist_cols = hs.hoist_cols
+    assert hs.k_h == 512 + lay.k_pad - hoist_cols and hoist_cols == 1024 + 2 * 7 * 128
     for image in (0, 1):
         for res, begin, count in ((32, 0, 32 ** 3), (40, 12345, 20000), (33, 77, 3000), (64, 64 * 64 * 5 + 13, 500)):
-            Xh = hs.gather_grid(image, res, begin, count).float()
-            full = hotpath.gather_grid_features(ctx, image, res, begin, count).float()
-            assert torch.equal(Xh[:, 512:], full[:, hoist_cols:]), (res, begin)
+            Xh_raw = hs.gather_grid(image, res, begin, count)
+            Xh = Xh_raw.float()
+            full_raw = hotpath.gather_grid_features(ctx, image, res, begin, count)
+            assert torch.equal(Xh[:, 512:], full_raw.float()[:, hoist_cols:]), (res, begin)
             full32 = hotpath.gather_grid_features(ctx32, image, res, begin, count)
-            want = full32[:, :hoist_cols] @ kw32.w0[:, :hoist_cols].t()
+            want = full32[:, :hoist_cols] @ kw32.w0[:, :hoist_cols].t() + kw32.b0
             err = (Xh[:, :512] - want).abs().max().item()
             scale = want.abs().max().item()
-            print(f"addend image {image} res {res}: max err {err:.3e} (max |addend| {scale:.3f})")
-            assert err <= 2e-2 * max(scale, 1.0)
+            sdf_h = hs.mlp(Xh_raw)
+            sdf_f = hotpath.mlp(kw, full_raw)
+            d_sdf = (sdf_h - sdf_f).abs().max().item()
+            print(f"image {image} res {res}: addend max err {err:.3e} (max |addend| {scale:.3f}), hoisted vs full MLP {d_sdf:.3e}")
+            assert err <= 1e-2 * max(scale, 1.0)
+            assert d_sdf <= 5e-3                      # both are bf16 evaluations of the same network output (O(0.1))
+    # parts: the two gather kernels write disjoint column ranges
+    a = torch.zeros(1000, hs.k_h, device=DEV, dtype=torch.bfloat16)
+    hs.gather_grid(0, 32, 100, 1000, parts=1, out=a)
+    assert torch.equal(a[:, 512:], torch.zeros_like(a[:, 512:])) and a[:, :512].abs().sum() > 0
+    b = torch.zeros(1000, hs.k_h, device=DEV, dtype=torch.bfloat16)
+    hs.gather_grid(0, 32, 100, 1000, parts=2, out=b)
+    assert torch.equal(b[:, :512], torch.zeros_like(b[:, :512]))
+    assert torch.equal(a + b, hs.gather_grid(0, 32, 100, 1000))
 
 
 def test_hoisted_grid_sdf_vs_oracle_and_unhoisted(monkeypatch):
