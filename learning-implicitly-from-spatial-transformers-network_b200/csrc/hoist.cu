@@ -553,21 +553,26 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       }
     }
   }
-  // ---- tail: scalar levels, q, zero pad.  item = (step, 8-column group); groups beyond the q columns are zeros ----
+  // ---- tail: scalar levels, q, zero pad.  item = (step, 8-column group); the groups beyond the q columns are zeros
+  //      and are enumerated separately so that a warp never mixes the two kinds ----
   {
     const int ngrp = (p.k_h - p.tail0) >> 3;             // tail0 and k_h are multiples of 8
-    const int nlive = (nscal + 3 + 7) >> 3;              // groups holding scalar-level or q columns
-    const float inv_ngrp = 1.0f / static_cast<float>(ngrp);
-    const int total = nsteps * ngrp;
-    for (int it = tid; it < total; it += kRestThreads) {
-      const int sr = fast_div(it, inv_ngrp);
-      const int gq = it - sr * ngrp;
-      const int s = t.s_lo + sr;
-      __nv_bfloat16* drow = Xb + static_cast<int64_t>(sr) * p.ldx + p.tail0 + gq * 8;
-      if (gq >= nlive) {
-        *reinterpret_cast<uint4*>(drow) = make_uint4(0u, 0u, 0u, 0u);
-        continue;
+    const int nlive = min(ngrp, (nscal + 3 + 7) >> 3);   // groups holding scalar-level or q columns
+    const int ndead = ngrp - nlive;
+    __nv_bfloat16* __restrict__ Xt = Xb + p.tail0;
+    if (ndead > 0) {
+      const float inv = 1.0f / static_cast<float>(ndead);
+      for (int it = tid; it < nsteps * ndead; it += kRestThreads) {
+        const int sr = fast_div(it, inv);
+        const int gq = nlive + it - sr * ndead;
+        *reinterpret_cast<uint4*>(Xt + static_cast<int64_t>(sr) * p.ldx + gq * 8) = make_uint4(0u, 0u, 0u, 0u);
       }
+    }
+    const float inv_live = 1.0f / static_cast<float>(nlive);
+    for (int it = tid; it < nsteps * nlive; it += kRestThreads) {
+      const int sr = fast_div(it, inv_live);
+      const int gq = it - sr * nlive;
+      const int s = t.s_lo + sr;
       float out[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -587,7 +592,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         }
         out[j] = val;
       }
-      store8(drow, out);
+      store8(Xt + static_cast<int64_t>(sr) * p.ldx + gq * 8, out);
     }
   }
 }
