@@ -232,6 +232,12 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
+    def traffic_of(name):
+        """dram bytes of one launch of `name` (ncu capture in profiles/, scaled to this run's rows per launch)."""
+        e = traffic.get(name)
+        if isinstance(e, dict) and e.get("rows"):
+            return e["dram_bytes"] / e["rows"] * chunk
+        return None
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # fused-kernel timing below
     roof_fused = None
     if fused:
@@ -246,7 +252,7 @@ def main():
         t_fused = sorted(tf)[1]
         fl = FLOP_PER_QUERY * count / (t_fused * 1e-3) / 1e12
         roof_fused = {"kernel": "sdf_fused_kernel", "bound": "tensor", "achieved": fl, "peak": pk["tensor"],
-                      "unit": "TFLOP/s", "frac": fl / pk["tensor"], "traffic": traffic.get("fused"),
+                      "unit": "TFLOP/s", "frac": fl / pk["tensor"], "traffic": traffic_of("sdf_fused_kernel"),
                       "ms_per_step": t_fused, "launches_per_step": 1, "peak_source": pk["src"],
                       "note": "gather fused into the MLP kernel: feature rows never reach HBM, compulsory HBM bytes "
                               "are 4 B/query of SDF + one read of the per-image tensors; reported against the "
@@ -317,7 +323,7 @@ def main():
     mlp_tflops = flop_exec * count / (t_mlp * 1e-3) / 1e12
     roof_mlp = {"kernel": "mlp_tc_kernel" if a.dtype == "bf16" else "sgemm_kernel", "bound": "tensor",
                 "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
-                "traffic": traffic.get("mlp_tc_kernel"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
+                "traffic": traffic_of("mlp_tc_kernel"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
                 "flop_per_query": flop_exec, "effective": FLOP_PER_QUERY * count / (t_mlp * 1e-3) / 1e12,
                 "peak_source": pk["src"]}
     if mlp_note:
@@ -326,7 +332,7 @@ def main():
     for name, tk, nb, what in gathers:
         gbs = nb / (tk * 1e-3) / 1e9
         roofs.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
-                      "frac": gbs / pk["hbm"], "traffic": traffic.get(name), "ms_per_step": tk,
+                      "frac": gbs / pk["hbm"], "traffic": traffic_of(name), "ms_per_step": tk,
                       "launches_per_step": n_chunks, "bytes_per_step": nb, "what": what, "peak_source": pk["src"]})
     roofs.sort(key=lambda r: -r["ms_per_step"])
     if fused:

@@ -5,6 +5,7 @@ import csv, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r01"
+ROWS = int(sys.argv[2]) if len(sys.argv) > 2 else 262144      # rows of the captured launch (scripts/gpu_ncu_hoist.sh: --chunk 262144)
 KERNELS = {"hoist_addend": "hoist_addend_kernel", "hoist_rest": "hoist_rest_kernel", "mlp_tc": "mlp_tc_kernel"}
 UNIT = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
@@ -31,8 +32,9 @@ for short, kernel in KERNELS.items():
             if k.startswith(name + " ["):
                 return float(v.replace(",", "")) * UNIT[k[len(name) + 2:-1]]
         return None
-    traffic[kernel] = get("dram__bytes_read.sum") + get("dram__bytes_write.sum")
+    traffic[kernel] = {"dram_bytes": get("dram__bytes_read.sum") + get("dram__bytes_write.sum"), "rows": ROWS}
     print(kernel, "dram bytes/launch", traffic[kernel], "->", dst)
-traffic["_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over a 262144-row chunk of the 256^3 grid, from the "
-                    f"ncu --set full captures in profiles/{TAG}_ncu_full_*.json (bench.py --chunk 262144)")
+traffic["_note"] = (f"dram__bytes_read.sum + dram__bytes_write.sum of ONE launch over a {ROWS}-row chunk of the 256^3 grid, from the "
+                    f"ncu --set full captures in profiles/{TAG}_ncu_full_*.json (bench.py --chunk {ROWS}); bench.py scales it "
+                    "linearly to the rows of its own launches")
 json.dump(traffic, open(os.path.join(ROOT, "profiles", "traffic.json"), "w"), indent=1)
