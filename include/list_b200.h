@@ -212,6 +212,21 @@ LIST_API int list_sdf_grid_host(const float* const* maps_nchw_host, const int32_
                        int64_t begin, int64_t count, float sdf_scale, int64_t chunk_rows,
                        float* sdf_host, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
+/* GPU marching cubes of a dense res^3 SDF grid (reference utils.py:172-182 hands the grid to
+ * PyMCubes on the host: `mcubes.marching_cubes(-grid, 0)`).  Two calls because the output size is data dependent:
+ *   list_mc_count     classifies cubes / grid edges, scans, and writes counts[0] = vertices, counts[1] = triangles
+ *                     (DEVICE int64[2]; the caller reads them back and allocates the outputs)
+ *   list_mc_generate  vertices[n][3] fp32 in index coordinates (i, j, k of sdf[i][j][k], like PyMCubes) -- one shared
+ *                     vertex per crossed grid edge, ascending edge order -- and triangles[n][3] int32, ascending cube order
+ * negate != 0 contours -sdf (what the reference passes).  workspace: >= list_mc_workspace_bytes(res), 256B aligned,
+ * untouched between the two calls.  Case tables: csrc/mc_tables.h (scripts/gen_mc_tables.py). */
+LIST_API size_t list_mc_workspace_bytes(int32_t res);
+LIST_API int list_mc_count(const float* sdf, int32_t res, float iso, int32_t negate, void* workspace, size_t workspace_bytes,
+                  int64_t* counts, void* stream);
+LIST_API int list_mc_generate(const float* sdf, int32_t res, float iso, int32_t negate, const void* workspace,
+                     size_t workspace_bytes, float* vertices, int64_t n_vertices, int32_t* triangles,
+                     int64_t n_triangles, void* stream);
+
 /* a-9 backward of a-2..a-6 for training (reference train.py:72-85 via autograd):
  * given d_sdf[B*N] computes all gradients in ListGrads (fp32 path only).
  * Needs the fp32 feature rows X and the saved activations in `workspace` from

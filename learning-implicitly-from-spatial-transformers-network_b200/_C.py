@@ -85,6 +85,9 @@ SIGNATURES = {
     "list_sdf_grid_host": (C.c_int, [_P(_vp), _P(_i32), _P(_i32), _i32, _i32, _P(_vp), _i32, _P(_i32), _P(_i32), _vp,
                                      _i32, _i32, _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _f32, _i64, _vp, _vp,
                                      _sz, _vp]),
+    "list_mc_workspace_bytes": (_sz, [_i32]),
+    "list_mc_count": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _sz, _vp, _vp]),
+    "list_mc_generate": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _sz, _vp, _i64, _vp, _i64, _vp]),
     "list_bwd_workspace_bytes": (_sz, [_P(ListWeights), _i64]),
     "list_sdf_bwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _P(ListGrads),
                                _vp, _sz, _vp]),

@@ -388,6 +388,33 @@ class HostGridRunner:
         return self.out
 
 
+# ------------------------------------------------------------------------------ mesh extraction
+def marching_cubes(grid: torch.Tensor, iso: float = 0.0, negate: bool = True):
+    """GPU marching cubes of a dense (res, res, res) fp32 grid on the device (csrc/mcubes.cu).  With negate=True it
+    contours -grid, which is what the reference hands to PyMCubes (utils.py:173).  Returns (vertices (nv, 3) fp32 in
+    index coordinates, triangles (nt, 3) int32), both on the device; one host read of the two counts in between."""
+    dev = _require_cuda(grid)
+    if grid.dim() != 3 or not (grid.shape[0] == grid.shape[1] == grid.shape[2]) or grid.dtype != torch.float32:
+        raise ValueError("marching_cubes expects a (res, res, res) float32 tensor")
+    g = grid.contiguous()
+    res = g.shape[0]
+    lib = _C.lib()
+    need = lib.list_mc_workspace_bytes(res)
+    if need == 0:
+        raise ValueError(f"marching_cubes: res {res} outside [2, 1024]")
+    ws = torch.empty(need, device=dev, dtype=torch.uint8)
+    counts = torch.zeros(2, device=dev, dtype=torch.int64)
+    with torch.cuda.device(dev):
+        _C.check(lib.list_mc_count(g.data_ptr(), res, float(iso), int(negate), ws.data_ptr(), need, counts.data_ptr(),
+                                   _stream()), "list_mc_count")
+        nv, nt = (int(x) for x in counts.cpu())
+        verts = torch.empty(nv, 3, device=dev, dtype=torch.float32)
+        tris = torch.empty(nt, 3, device=dev, dtype=torch.int32)
+        _C.check(lib.list_mc_generate(g.data_ptr(), res, float(iso), int(negate), ws.data_ptr(), need, verts.data_ptr(), nv,
+                                      tris.data_ptr(), nt, _stream()), "list_mc_generate")
+    return verts, tris
+
+
 # ------------------------------------------------------------------------------ training (fwd + bwd)
 class _SdfFunction(torch.autograd.Function):
     """Rows a-2..a-6 + a-9 as one autograd node (fp32).  Inputs are the channels-last per-image

@@ -11,7 +11,9 @@ What changed underneath (rows a-8 / §8e):
   * under torch.distributed the grid is sharded by contiguous point ranges across ranks and
     gathered with one collective;
   * `grid_res` (default = vox_res) decouples the query grid from the voxel resolution, which the
-    reference ties together (executors.py:192-193,229).
+    reference ties together (executors.py:192-193,229);
+  * the mesh is extracted by GPU marching cubes from the grid still on the device (csrc/mcubes.cu) instead of
+    PyMCubes on the host (utils.py:172-182).
 """
 from __future__ import annotations
 
@@ -82,12 +84,13 @@ class LIST:
             # reference's 65 536-point chunks: the last partial wave of gather CTAs is amortised
             lambda begin, count: net.grid(ctx, res, begin, count, self.sdf_scale, max(self.test_pointnum, 524288)),
             total, align=res * res)
-        vals = grid[0].view(res, res, res).cpu().numpy()
+        self._grid_dev = grid[0].view(res, res, res)                  # kept on the device for the mesh extraction
+        vals = self._grid_dev.cpu().numpy()
         return vals, ctx
 
     def test(self, batch, eval_pred=False):
         vals, ctx = self.predict_grid(batch)
-        mesh = generate_mesh(vals, self.bb_min, self.bb_max)
+        mesh = generate_mesh(self._grid_dev, self.bb_min, self.bb_max)
         scores = self.eval(mesh, batch.get("gt_mesh")) if eval_pred else {}
         occ = None
         return [mesh, occ, ctx.occ_pred.squeeze(1)], scores
@@ -98,21 +101,38 @@ class LIST:
 
     def save(self, batch, pred, fname):
         mesh = pred[0]
-        if mesh is None:
-            raise RuntimeError("no mesh to save: PyMCubes/trimesh are not installed; use predict_grid()")
         mesh.export(fname + "_pred.obj")
 
 
-def generate_mesh(gridvalues: np.ndarray, bb_min: float, bb_max: float):
-    """utils.generate_mesh (utils.py:172-182): marching cubes of -grid at 0 through PyMCubes, when the
-    optional host libraries are present; returns None otherwise (GPU marching cubes is a §8f row)."""
+class Mesh:
+    """Minimal stand-in for trimesh.Trimesh (not installed here): vertices (n, 3) float, faces (m, 3) int, OBJ export."""
+
+    def __init__(self, vertices: np.ndarray, faces: np.ndarray):
+        self.vertices, self.faces = np.asarray(vertices), np.asarray(faces)
+
+    def export(self, fname: str) -> None:
+        with open(fname, "w") as f:
+            for v in self.vertices:
+                f.write(f"v {v[0]:.6f} {v[1]:.6f} {v[2]:.6f}\n")
+            for t in self.faces + 1:
+                f.write(f"f {t[0]} {t[1]} {t[2]}\n")
+
+
+def generate_mesh(gridvalues, bb_min: float, bb_max: float):
+    """utils.generate_mesh (utils.py:172-182): marching cubes of -grid at 0, then the reference's vertex
+    normalisation `(v - v.min()) / v.max() * (bb_max - bb_min) + bb_min` (for more than 10 vertices).
+    The extraction runs on the GPU (hotpath.marching_cubes) instead of PyMCubes on the host; the result is a
+    trimesh.Trimesh when trimesh is installed, else a `Mesh` with the same `.vertices/.faces/.export`."""
+    grid = gridvalues if isinstance(gridvalues, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(gridvalues))
+    if not grid.is_cuda:
+        grid = grid.cuda()
+    verts, tris = hotpath.marching_cubes(grid.float(), 0.0, negate=True)
+    if verts.shape[0] > 10:
+        verts = (verts - verts.min()) / verts.max()
+        verts = verts * (bb_max - bb_min) + bb_min
+    v, t = verts.cpu().numpy(), tris.cpu().numpy()
     try:
-        import mcubes
         import trimesh
+        return trimesh.Trimesh(v, t)
     except ImportError:
-        return None
-    vertices, triangles = mcubes.marching_cubes(-1.0 * gridvalues, 0)
-    if len(vertices) > 10:
-        vertices = (vertices - vertices.min()) / vertices.max()
-        vertices = vertices * (bb_max - bb_min) + bb_min
-    return trimesh.Trimesh(vertices, triangles)
+        return Mesh(v, t)
