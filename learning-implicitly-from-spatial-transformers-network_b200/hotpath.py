@@ -476,6 +476,65 @@ class _SdfFunction(torch.autograd.Function):
                 d_w3.view(s3), d_b3, *d_vols)
 
 
+class _PrepVolumeFn(torch.autograd.Function):
+    """NCDHW fp32 volume -> channels-last (B,R,R,R,C) through list_prep_volume; the backward is the inverse
+    permutation as a VIEW (no copy), so autograd continues into the voxel encoder."""
+
+    @staticmethod
+    def forward(ctx, vol):
+        dev = _require_cuda(vol)
+        v = vol.detach().to(torch.float32).contiguous()
+        B, Cc, R = v.shape[0], v.shape[1], v.shape[2]
+        out = torch.empty(B, R, R, R, Cc, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _C.check(_C.lib().list_prep_volume(v.data_ptr(), B, Cc, R, out.data_ptr(), _C.F32, _stream()), "list_prep_volume")
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.permute(0, 4, 1, 2, 3)
+
+
+class _PrepMapsFn(torch.autograd.Function):
+    """The five NCHW maps -> ONE upsampled channels-last (B,S,S,1024) tensor through list_prep_maps (row a-1, reference
+    modules.py:25-35); the backward splits the gradient per map and runs ATen's bilinear-upsample adjoint on it."""
+
+    @staticmethod
+    def forward(ctx, map_size, *maps):
+        dev = _require_cuda(*maps)
+        ms = [m.detach().to(torch.float32).contiguous() for m in maps]
+        B = ms[0].shape[0]
+        cm = sum(m.shape[1] for m in ms)
+        out = torch.empty(B, map_size, map_size, cm, device=dev, dtype=torch.float32)
+        with torch.cuda.device(dev):
+            _C.check(_C.lib().list_prep_maps(_C.ptr_array([m.data_ptr() for m in ms]), _C.i32_array([m.shape[1] for m in ms]),
+                                             _C.i32_array([m.shape[2] for m in ms]), len(ms), B, map_size, out.data_ptr(),
+                                             _C.F32, _stream()), "list_prep_maps")
+        ctx.shapes = [tuple(m.shape) for m in ms]
+        ctx.map_size = map_size
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        S = ctx.map_size
+        grads, c0 = [], 0
+        for shp in ctx.shapes:
+            gi = g[..., c0:c0 + shp[1]].permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
+            grads.append(torch.ops.aten.upsample_bilinear2d_backward(gi, [S, S], list(shp), True, None, None))
+            c0 += shp[1]
+        return (None, *grads)
+
+
+def prep_maps_autograd(maps: Sequence[torch.Tensor], map_size: int = MAP_SIZE) -> torch.Tensor:
+    """Differentiable a-1 + layout: (B,C_i,H_i,W_i) maps -> (B,S,S,sum C) fp32 channels-last."""
+    return _PrepMapsFn.apply(map_size, *maps)
+
+
+def prep_volume_autograd(vol: torch.Tensor) -> torch.Tensor:
+    """Differentiable layout change (B,C,R,R,R) -> (B,R,R,R,C) fp32."""
+    return _PrepVolumeFn.apply(vol)
+
+
 def query_sdf_autograd(points, trans_mat, maps_cl, vols_cl, params: dict, raw: bool = True, prefix: str = "fc."):
     """Differentiable a-7: `params` maps the reference's state_dict names to the master tensors."""
     p = params

@@ -110,9 +110,9 @@ class LIST(nn.Module):
         if not torch.is_grad_enabled():
             ctx = hotpath.prepare_context(maps, vols, T, self.compute_dtype)
             return vols[0], self.query(ctx, query)
-        # channels-last views built with differentiable torch ops so autograd reaches the encoders
-        ups = [F.interpolate(m, size=self.percep_pooling.map_size, mode="bilinear", align_corners=True) for m in maps]
-        maps_cl = torch.cat(ups, dim=1).permute(0, 2, 3, 1).contiguous()
-        vols_cl = [v.permute(0, 2, 3, 4, 1).contiguous() for v in vols]
+        # kernel layouts through differentiable prep functions (one pass each, no torch.cat / permute copies), so
+        # autograd reaches the encoders
+        maps_cl = hotpath.prep_maps_autograd(maps, self.percep_pooling.map_size)
+        vols_cl = [hotpath.prep_volume_autograd(v) for v in vols]
         sdf = hotpath.query_sdf_autograd(query, T, maps_cl, vols_cl, self.sdf_decoder.param_dict(), raw=True)
         return vols[0], sdf

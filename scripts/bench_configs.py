@@ -45,9 +45,8 @@ def cfg2():
     def step():
         for t in leaves:
             t.grad = None
-        ups = [torch.nn.functional.interpolate(m, size=137, mode="bilinear", align_corners=True) for m in maps]
-        maps_cl = torch.cat(ups, dim=1).permute(0, 2, 3, 1).contiguous()
-        vols_cl = [v.permute(0, 2, 3, 4, 1).contiguous() for v in vols]
+        maps_cl = hotpath.prep_maps_autograd(maps)                     # as models.LIST.forward
+        vols_cl = [hotpath.prep_volume_autograd(v) for v in vols]
         sdf = hotpath.query_sdf_autograd(g.points, T, maps_cl, vols_cl, w, raw=True)
         loss = ((gt * scale - sdf) ** 2).sum(-1).mean()             # reference losses.py:21-27
         loss.backward()
@@ -64,7 +63,7 @@ def cfg2():
     return {"config": "cfg-2: 8 images x 2048 sampled queries (0.45/0.44/0.1, sdf_scale 10), fwd+bwd, fp32, 1 B200",
             "ms_per_step": ms, "queries_per_sec": B * N / (ms * 1e-3), "loss": loss,
             "ms_fwd_inference_path": ms_fwd,
-            "note": "step = differentiable upsample/layout glue (torch) + list_sdf_fwd kernels + SDF loss + list_sdf_bwd kernels "
+            "note": "step = differentiable prep kernels (upsample + layouts) + list_sdf_fwd kernels + SDF loss + list_sdf_bwd kernels "
                     "(gradients w.r.t. MLP weights, 6 volumes, 5 maps, trans_mat)"}
 
 

@@ -267,7 +267,8 @@ def test_full_size_256_grid_slab_properties():
 
 
 # ------------------------------------------------------------------ backward (a-9)
-def test_backward_vs_reference_golden():
+@pytest.mark.parametrize("glue", ["torch", "prep_fn"])
+def test_backward_vs_reference_golden(glue):
     z = np.load(os.path.join(GOLDEN, "grad_small_b2.npz"))
     kw_ = json.loads(str(z["recipe"]))
     inp = synth.make_inputs(**kw_)
@@ -277,9 +278,13 @@ def test_backward_vs_reference_golden():
     vols = [v.clone().requires_grad_(True) for v in g.vols]
     T = g.trans_mat.clone().requires_grad_(True)
     w = {k: v.clone().requires_grad_(True) for k, v in g.weights.items()}
-    ups = [torch.nn.functional.interpolate(m, size=137, mode="bilinear", align_corners=True) for m in maps]
-    maps_cl = torch.cat(ups, dim=1).permute(0, 2, 3, 1).contiguous()
-    vols_cl = [v.permute(0, 2, 3, 4, 1).contiguous() for v in vols]
+    if glue == "torch":            # layouts built with stock differentiable torch ops
+        ups = [torch.nn.functional.interpolate(m, size=137, mode="bilinear", align_corners=True) for m in maps]
+        maps_cl = torch.cat(ups, dim=1).permute(0, 2, 3, 1).contiguous()
+        vols_cl = [v.permute(0, 2, 3, 4, 1).contiguous() for v in vols]
+    else:                          # what models.LIST.forward uses: the prep kernels as autograd functions
+        maps_cl = hotpath.prep_maps_autograd(maps)
+        vols_cl = [hotpath.prep_volume_autograd(v) for v in vols]
     sdf = hotpath.query_sdf_autograd(g.points, T, maps_cl, vols_cl, w, raw=True)
     assert np.abs(sdf.detach().cpu().numpy() - z["sdf"]).max() <= FP32_TOL
     loss = ((sdf_gt.to(DEV) * float(z["sdf_scale"]) - sdf) ** 2).sum(-1).mean()
