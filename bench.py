@@ -361,8 +361,8 @@ def main():
     e2e = None
     if not a.no_e2e:
         pin = lambda t: t.contiguous().pin_memory()
-        runner = hotpath.HostGridRunner([pin(m) for m in inp.maps], [pin(v) for v in inp.vols], pin(inp.trans_mat), kw,
-                                        res, begin, count, a.dtype, chunk)
+        runner = parallel.ShardedHostRunner([pin(m) for m in inp.maps], [pin(v) for v in inp.vols], pin(inp.trans_mat), kw,
+                                            res, a.dtype, chunk)
         for _ in range(2):
             runner.run(SDF_SCALE)
         sync()
@@ -378,8 +378,10 @@ def main():
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         e2e = {"value": total * e_steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
                "d2h_bytes_per_step": runner.d2h_bytes, "steps": e_steps,
-               "what": "list_sdf_grid_host: pinned host per-image tensors -> H2D -> prep kernels -> gather+MLP over "
-                       "the rank's grid shard -> D2H of its SDF values; max over ranks"}
+               "what": "parallel.ShardedHostRunner: pinned host per-image tensors (fp32, reference layout) -> H2D "
+                       + ("(1/N of every tensor per rank + one NCCL all_gather over NVLink) " if world > 1 else "")
+                       + "-> prep kernels -> projection + gather + MLP over the rank's grid shard -> D2H of its SDF values "
+                       "into pinned host memory; wall clock, max over ranks"}
         # sanity: same numbers as the resident path
         assert torch.equal(host_out, local_out.cpu()), "host path and resident path disagree"
 

@@ -39,3 +39,81 @@ def sharded_grid(evaluate: Callable[[int, int], torch.Tensor], total: int, align
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     begin, count = shard_range(total, rank, world, align)
     return gather_shards(evaluate(begin, count), total, world, align, group)
+
+
+def slice_bounds(numel: int, per: int, rank: int) -> Tuple[int, int]:
+    """[lo, hi) of `rank`'s slice of a flattened tensor cut into pieces of `per` elements."""
+    lo = min(numel, rank * per)
+    return lo, min(numel, lo + per)
+
+
+def rebuild_from_gathered(gathered: torch.Tensor, per, fulls) -> None:
+    """gathered: (world, sum(per)) rank-major slices of every tensor (each padded to per[i]); writes the
+    reassembled tensors into `fulls` in place."""
+    off = 0
+    for d, p in zip(fulls, per):
+        d.view(-1).copy_(gathered[:, off:off + p].reshape(-1)[:d.numel()])
+        off += p
+
+
+class ShardedHostRunner:
+    """End-to-end dense-grid evaluation from HOST buffers on `world` ranks (bench.py's e2e leg):
+    pinned reference-layout per-image tensors -> device -> prep kernels -> this rank's shard of the grid -> pinned
+    host shard.  With one rank every tensor is uploaded whole.  With several, uploading the same 206 MB on every rank
+    would make the step PCIe-bound, so each rank uploads 1/world of every tensor and ONE all_gather over NVLink
+    rebuilds the full set on every GPU (the per-image tensors are replicated, the grid is what is sharded)."""
+
+    def __init__(self, maps_host, vols_host, trans_host, weights, res: int, dtype="bf16", chunk_rows: int = 1048576,
+                 group=None):
+        from . import hotpath
+        self.hotpath = hotpath
+        self.group = group
+        ddp = dist.is_available() and dist.is_initialized()
+        self.rank = dist.get_rank(group) if ddp else 0
+        self.world = dist.get_world_size(group) if ddp else 1
+        self.hosts = [*maps_host, *vols_host, trans_host]
+        for t in self.hosts:
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or not t.is_pinned():
+                raise ValueError("host inputs must be contiguous, pinned fp32 CPU tensors")
+        self.n_maps = len(maps_host)
+        self.weights, self.res, self.dtype = weights, res, dtype
+        dev = weights.w0.device
+        self.dev = dev
+        total = res ** 3
+        self.begin, self.count = shard_range(total, self.rank, self.world, align=res * res)
+        self.chunk = max(1, min(chunk_rows, self.count))
+        self.full = [torch.empty(t.shape, device=dev, dtype=torch.float32) for t in self.hosts]
+        self.out_dev = torch.empty(trans_host.shape[0], self.count, device=dev, dtype=torch.float32)
+        self.out_host = torch.empty(trans_host.shape[0], self.count, dtype=torch.float32).pin_memory()
+        self.per = [-(-t.numel() // self.world) for t in self.hosts]           # elements of every rank's slice
+        if self.world > 1:
+            self.mine = torch.zeros(sum(self.per), device=dev, dtype=torch.float32)
+            self.gathered = torch.empty(self.world, sum(self.per), device=dev, dtype=torch.float32)
+        self.h2d_bytes = sum((slice_bounds(t.numel(), p, self.rank)[1] - slice_bounds(t.numel(), p, self.rank)[0]) * 4
+                             for t, p in zip(self.hosts, self.per))
+        self.d2h_bytes = self.out_host.numel() * 4
+        self.workspace = None
+
+    def run(self, sdf_scale: float = 1.0) -> torch.Tensor:
+        hp = self.hotpath
+        if self.world == 1:
+            for d, h in zip(self.full, self.hosts):
+                d.copy_(h, non_blocking=True)
+        else:
+            off = 0
+            for h, p in zip(self.hosts, self.per):
+                flat = h.view(-1)
+                lo, hi = slice_bounds(flat.numel(), p, self.rank)
+                if hi > lo:
+                    self.mine[off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
+                off += p
+            dist.all_gather_into_tensor(self.gathered.view(-1), self.mine, group=self.group)
+            rebuild_from_gathered(self.gathered, self.per, self.full)
+        maps, vols, T = self.full[:self.n_maps], self.full[self.n_maps:-1], self.full[-1]
+        ctx = hp.prepare_context(maps, vols, T, self.dtype)
+        if self.workspace is None:
+            self.workspace = hp._workspace(ctx.struct(), self.weights.struct(), self.chunk, self.dev)
+        hp.grid_sdf(ctx, self.weights, self.res, self.begin, self.count, sdf_scale, self.chunk, out=self.out_dev,
+                    workspace=self.workspace)
+        self.out_host.copy_(self.out_dev, non_blocking=True)
+        return self.out_host

@@ -61,3 +61,24 @@ def test_sharded_grid_gloo_world2(total, align):
         p.join(timeout=60)
     assert all(ok for _, ok, _ in res), res
     assert all(shape == (2, total) for _, _, shape in res)
+
+
+def test_sliced_upload_reassembles_every_tensor():
+    """ShardedHostRunner's H2D scheme: every rank uploads 1/world of each tensor, one all_gather, then reassembly."""
+    import torch
+    from list_b200 import parallel
+    g = torch.Generator().manual_seed(0)
+    tensors = [torch.rand(3, 5, 7, generator=g), torch.rand(11, generator=g), torch.rand(1, 4, 3, generator=g), torch.rand(2, 2, generator=g)]
+    for world in (1, 2, 3, 8):
+        per = [-(-t.numel() // world) for t in tensors]
+        gathered = torch.zeros(world, sum(per))
+        for rank in range(world):
+            off = 0
+            for t, p in zip(tensors, per):
+                lo, hi = parallel.slice_bounds(t.numel(), p, rank)
+                gathered[rank, off:off + hi - lo] = t.view(-1)[lo:hi]
+                off += p
+        fulls = [torch.empty_like(t) for t in tensors]
+        parallel.rebuild_from_gathered(gathered, per, fulls)
+        for a, b in zip(fulls, tensors):
+            assert torch.equal(a, b)
