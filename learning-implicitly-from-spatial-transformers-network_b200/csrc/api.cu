@@ -44,7 +44,7 @@ int gather_bwd(const ListCtx* ctx, const float* q, int q_is_raw, int B, int64_t 
 int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
                float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
 int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
-                       float out_div, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
+                       float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
 int sdf_grid_fused(const ListCtx* ctx, const ListWeights* w, int image, int res, double bb_min, double bb_max,
                    int64_t begin, int64_t count, float* sdf, float out_div, cudaStream_t st);
 
@@ -406,7 +406,7 @@ int list_mlp_hoisted_fwd(const ListWeights* w, int32_t hoist_cols, const void* X
   LIST_CHECK_ARG(Xh && sdf && out_div != 0.f, "list_mlp_hoisted_fwd: X/sdf NULL or out_div == 0");
   LIST_CHECK_ARG(hoist_cols > 0 && hoist_cols < w->k_pad && hoist_cols % 64 == 0, "list_mlp_hoisted_fwd: hoist_cols %d invalid for k_pad %d",
                  hoist_cols, w->k_pad);
-  return mlp_tc_fwd_hoisted(w, hoist_cols, w->k_pad - hoist_cols, Xh, ldx, rows, sdf, out_div, nullptr, nullptr, nullptr,
+  return mlp_tc_fwd_hoisted(w, hoist_cols, w->k_pad - hoist_cols, Xh, ldx, rows, sdf, out_div, mlp_variant(), nullptr, nullptr, nullptr,
                             static_cast<cudaStream_t>(stream));
 }
 
@@ -552,7 +552,7 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
           int b; int64_t n0, n;
           span(i, b, n0, n);
           return mlp_tc_fwd_hoisted(w, pl.hoist_cols, pl.k_h - 512, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0,
-                                    sdf_scale, nullptr, nullptr, nullptr, s);
+                                    sdf_scale, mlp_variant(), nullptr, nullptr, nullptr, s);
         });
   }
   return run_chunks(

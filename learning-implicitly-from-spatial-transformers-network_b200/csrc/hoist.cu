@@ -776,12 +776,15 @@ int gather(const ListCtx* ctx, const ListWeights* w, const Plan& pl, const void*
 
   static const int vec = []() { const char* e = getenv("LIST_B200_HOIST_VEC"); return (e && e[0] == '8') ? 8 : 4; }();
   if (parts & kPartAddend) {
+    LIST_CUDA(cudaFuncSetAttribute(hoist_addend_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    LIST_CUDA(cudaFuncSetAttribute(hoist_addend_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     if (vec == 8) hoist_addend_kernel<8><<<tile_count(a.tm), kN0 / 8, 0, st>>>(a);
     else hoist_addend_kernel<4><<<tile_count(a.tm), kN0 / 4, 0, st>>>(a);
     LIST_LAUNCH_CHECK("hoist_addend_kernel");
   }
   if (parts & kPartRest) {
     LIST_CUDA(cudaFuncSetAttribute(hoist_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    LIST_CUDA(cudaFuncSetAttribute(hoist_rest_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     hoist_rest_kernel<<<tile_count(r.tm), kRestThreads, smem, st>>>(r);
     LIST_LAUNCH_CHECK("hoist_rest_kernel");
   }

@@ -406,6 +406,9 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   LIST_CUDA(cudaGetDevice(&dev));
   LIST_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   LIST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CG, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+  // keep the SM's shared-memory carve-out at its maximum so that gather CTAs of the next chunk can co-reside (api.cu
+  // run_chunks); otherwise the carve-out is sized for this kernel alone and nothing else fits until the SM drains
+  LIST_CUDA(cudaFuncSetAttribute(mlp_tc_kernel<CG, ST>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
   const int64_t rows_per_tile = static_cast<int64_t>(BM) * CG;
   const int64_t tiles = (rows + rows_per_tile - 1) / rows_per_tile * (proj ? pa.groups : 1);
   const int clusters = static_cast<int>(tiles < (sms / CG) ? tiles : (sms / CG));
@@ -452,7 +455,7 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
 // Hoisted rows (hoist.cu): Xh[rows][ldx] = [addend n0 (incl. bias b0) | k columns]; fc_0 runs on W0[:, col0 : col0 + k]
 // only and the addend block is added to its accumulator in the epilogue; fc_1, fc_2, fc_out as in mlp_tc_fwd.
 int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
-                       float out_div, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
+                       float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
   if (rows == 0) return LIST_OK;
   LIST_CHECK_ARG(w->n0 == tc::N0 && w->n1 == tc::N1 && w->n2 == tc::N2,
                  "mlp_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
@@ -469,6 +472,7 @@ int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, in
   aa.ld = ldx;
   aa.k = k;
   const tc::ProjArgs none;
+  if (variant == 3) return tc::launch<2, 3>(&wv, xh + tc::N0, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, aa, st);
   return tc::launch<2, 4>(&wv, xh + tc::N0, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, aa, st);
 }
 
