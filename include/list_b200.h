@@ -190,6 +190,11 @@ LIST_API int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w
                                void* X, int64_t ldx, int32_t parts, void* stream);
 LIST_API int list_mlp_hoisted_fwd(const ListWeights* w, int32_t hoist_cols, const void* Xh, int64_t ldx, int64_t rows,
                          float* sdf, float out_div, void* stream);
+/* Diagnostic twin: additionally records the phase timeline of CTA 0 -- trace[16 tiles][12] device int64 clock64() stamps:
+ * 0 tile start, 1 fc_0 issued, 2 fc_1 start, 3 fc_1 issued, 4 fc_2 start, 5 fc_2 issued (MMA thread);
+ * 6 fc_0 done seen, 7 ep0 done, 8 fc_1 done seen, 9 ep1 done, 10 fc_2 done seen, 11 ep2 done (epilogue warp). */
+LIST_API int list_mlp_hoisted_trace(const ListWeights* w, int32_t hoist_cols, const void* Xh, int64_t ldx, int64_t rows,
+                           float* sdf, float out_div, int64_t* trace, void* stream);
 
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
  * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */

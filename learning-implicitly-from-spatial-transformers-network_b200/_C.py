@@ -76,6 +76,7 @@ SIGNATURES = {
     "list_hoist_layout": (C.c_int, [_P(ListCtx), _P(ListWeights), _P(_i32), _P(_i32)]),
     "list_hoist_prepare": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _sz, _vp]),
     "list_mlp_hoisted_fwd": (C.c_int, [_P(ListWeights), _i32, _vp, _i64, _i64, _vp, _f32, _vp]),
+    "list_mlp_hoisted_trace": (C.c_int, [_P(ListWeights), _i32, _vp, _i64, _i64, _vp, _f32, _vp, _vp]),
     "list_hoist_gather_grid_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _f64, _f64, _i64, _i64, _vp,
                                              _i64, _i32, _vp]),
     "list_sdf_workspace_bytes": (_sz, [_P(ListCtx), _P(ListWeights), _i64]),

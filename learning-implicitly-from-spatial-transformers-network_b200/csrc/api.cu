@@ -44,7 +44,7 @@ int gather_bwd(const ListCtx* ctx, const float* q, int q_is_raw, int B, int64_t 
 int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, int variant,
                float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
 int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
-                       float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
+                       float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, long long* trace, cudaStream_t st);
 int sdf_grid_fused(const ListCtx* ctx, const ListWeights* w, int image, int res, double bb_min, double bb_max,
                    int64_t begin, int64_t count, float* sdf, float out_div, cudaStream_t st);
 
@@ -407,7 +407,17 @@ int list_mlp_hoisted_fwd(const ListWeights* w, int32_t hoist_cols, const void* X
   LIST_CHECK_ARG(hoist_cols > 0 && hoist_cols < w->k_pad && hoist_cols % 64 == 0, "list_mlp_hoisted_fwd: hoist_cols %d invalid for k_pad %d",
                  hoist_cols, w->k_pad);
   return mlp_tc_fwd_hoisted(w, hoist_cols, w->k_pad - hoist_cols, Xh, ldx, rows, sdf, out_div, mlp_variant(), nullptr, nullptr, nullptr,
-                            static_cast<cudaStream_t>(stream));
+                            nullptr, static_cast<cudaStream_t>(stream));
+}
+
+int list_mlp_hoisted_trace(const ListWeights* w, int32_t hoist_cols, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
+                           float out_div, int64_t* trace, void* stream) {
+  int rc = check_weights(w, -1);
+  if (rc) return rc;
+  LIST_CHECK_ARG(w->dtype == LIST_BF16 && rows >= 1 && Xh && sdf && trace && out_div != 0.f, "list_mlp_hoisted_trace: bad arguments");
+  LIST_CHECK_ARG(hoist_cols > 0 && hoist_cols < w->k_pad && hoist_cols % 64 == 0, "list_mlp_hoisted_trace: hoist_cols %d invalid", hoist_cols);
+  return mlp_tc_fwd_hoisted(w, hoist_cols, w->k_pad - hoist_cols, Xh, ldx, rows, sdf, out_div, mlp_variant(), nullptr, nullptr, nullptr,
+                            reinterpret_cast<long long*>(trace), static_cast<cudaStream_t>(stream));
 }
 
 int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
@@ -552,7 +562,7 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
           int b; int64_t n0, n;
           span(i, b, n0, n);
           return mlp_tc_fwd_hoisted(w, pl.hoist_cols, pl.k_h - 512, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0,
-                                    sdf_scale, mlp_variant(), nullptr, nullptr, nullptr, s);
+                                    sdf_scale, mlp_variant(), nullptr, nullptr, nullptr, nullptr, s);
         });
   }
   return run_chunks(

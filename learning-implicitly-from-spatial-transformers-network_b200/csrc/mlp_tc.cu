@@ -53,7 +53,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ sdf,
               long long rows, int nk0, float out_div, float* __restrict__ dbg1, float* __restrict__ dbg2,
               float* __restrict__ dbg3, __nv_bfloat16* __restrict__ proj_out, int proj_groups, int proj_w_col_stride,
-              long long proj_out_group_stride, const __nv_bfloat16* __restrict__ addend, long long ld_add) {
+              long long proj_out_group_stride, const __nv_bfloat16* __restrict__ addend, long long ld_add,
+              long long* __restrict__ trace) {
   using C = Cfg<CG, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -84,6 +85,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   const bool proj = proj_out != nullptr;
   const int tiles_per_group = static_cast<int>((rows + rows_per_tile - 1) / rows_per_tile);
   const int num_tiles = proj ? tiles_per_group * proj_groups : tiles_per_group;
+
+  // Diagnostic phase timeline (list_mlp_hoisted_trace): CTA 0 stamps clock64() at the phase boundaries of its first
+  // kTraceTiles tiles: slots 0..5 by the MMA thread (tile start, fc_0 issued, fc_1 start, fc_1 issued, fc_2 start,
+  // fc_2 issued), slots 6..11 by epilogue warp 2 (fc_0 done seen, ep0 done, fc_1 done seen, ep1 done, fc_2 done seen, ep2 done).
+  constexpr int kTraceTiles = 16, kTraceSlots = 12;
+  const bool tracing = trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int tile_no, int slot) {
+    if (tracing && tile_no < kTraceTiles) trace[tile_no * kTraceSlots + slot] = clock64();
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmX);
@@ -164,10 +174,12 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       constexpr uint32_t kInstrB = (256 / CG) * BK * 2;             // bytes of B one N=256 instruction reads per CTA
       uint32_t slot = 0, hphase = 0;
       bool first = true;
-      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int tno = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tno) {
         if (!first) { mbar_wait(hready_bar, hphase); hphase ^= 1; }   // previous tile's accumulators drained
         first = false;
         tc_fence_after();
+        stamp(tno, 0);
         // ---- fc_0: D[0,512) = X · W0^T ----
         for (int kc = 0; kc < nk0; ++kc, ++slot) {
           const int s = slot % C::STAGES;
@@ -186,6 +198,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           umma_commit<CG>(empty_bar(s));
         }
         umma_commit<CG>(dfull_bar);
+        stamp(tno, 1);
         if (proj) continue;
         // ---- fc_1: D[256,512) = H1(TMEM [0,256)) · W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) · W2^T ----
 #pragma unroll 1
@@ -193,6 +206,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           const int nk = (layer == 1 ? N0 : N1) / BK;
           mbar_wait(hready_bar, hphase); hphase ^= 1;
           tc_fence_after();
+          stamp(tno, 2 * layer);
           for (int kc = 0; kc < nk; ++kc, ++slot) {
             const int s = slot % C::STAGES;
             mbar_wait(full_bar(s), (slot / C::STAGES) & 1);
@@ -207,6 +221,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             umma_commit<CG>(empty_bar(s));
           }
           umma_commit<CG>(dfull_bar);
+          stamp(tno, 2 * layer + 1);
         }
       }
     }
@@ -217,7 +232,9 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t hready_remote = (CG == 2) ? mapa(hready_bar, 0) : hready_bar;
     const float bias3 = __ldg(b3);
     uint32_t dphase = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int etno = 0;
+    const bool estamp = warp == kEpiWarp0 && lane == 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++etno) {
       const int group = tile / tiles_per_group;
       const long long row = (tile - group * tiles_per_group) * rows_per_tile + rank * BM + quarter * 32 + lane;
       // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
@@ -229,6 +246,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
+      if (estamp) stamp(etno, 6);
       if (proj) {                                           // raw accumulator -> bf16 row of the group's slab
         __nv_bfloat16* const orow = proj_out + group * proj_out_group_stride + row * N0;
 #pragma unroll 1
@@ -317,11 +335,13 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
       tmem_wait_st();
       tc_fence_before();
+      if (estamp) stamp(etno, 7);
       if (CG == 2) mbar_arrive_cluster(hready_remote);
       else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
       // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
+      if (estamp) stamp(etno, 8);
 #pragma unroll 1
       for (int j = 0; j < N1 / 32; ++j) {
         uint32_t v[32], u[16];
@@ -341,11 +361,13 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
       tmem_wait_st();
       tc_fence_before();
+      if (estamp) stamp(etno, 9);
       if (CG == 2) mbar_arrive_cluster(hready_remote);
       else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
       // ---- after fc_2: sdf = (relu(acc + b2) · w3 + b3) / out_div ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
+      if (estamp) stamp(etno, 10);
       float acc = 0.f;
 #pragma unroll 1
       for (int j = 0; j < N2 / 32; ++j) {
@@ -361,6 +383,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         }
       }
       tc_fence_before();
+      if (estamp) stamp(etno, 11);
       if (CG == 2) mbar_arrive_cluster(hready_remote);
       else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
       if (row < rows) sdf[row] = __fdiv_rn(acc + bias3, out_div);
@@ -381,6 +404,7 @@ struct AddArgs {                        // hoisted rows: fc_0 over k columns of 
   const __nv_bfloat16* addend = nullptr;
   int64_t ld = 0;
   int k = 0;                            // K of fc_0 (columns of X / of the W0 view); 0 = w->k_pad
+  long long* trace = nullptr;           // diagnostic phase timeline of CTA 0 (see the kernel)
 };
 struct ProjArgs {                       // projection mode (see the kernel); all zero = the full MLP
   __nv_bfloat16* out = nullptr;         // [groups][rows][512]
@@ -427,7 +451,7 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   const int nk0 = k0 / BK;
   LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG, ST>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
                                sdf, static_cast<long long>(rows), nk0, out_div, dbg1, dbg2, dbg3, pa.out, pa.groups,
-                               pa.w_col_stride, static_cast<long long>(rows) * N0, aa.addend, static_cast<long long>(aa.ld)));
+                               pa.w_col_stride, static_cast<long long>(rows) * N0, aa.addend, static_cast<long long>(aa.ld), aa.trace));
   return LIST_OK;
 }
 
@@ -455,7 +479,7 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
 // Hoisted rows (hoist.cu): Xh[rows][ldx] = [addend n0 (incl. bias b0) | k columns]; fc_0 runs on W0[:, col0 : col0 + k]
 // only and the addend block is added to its accumulator in the epilogue; fc_1, fc_2, fc_out as in mlp_tc_fwd.
 int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
-                       float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, cudaStream_t st) {
+                       float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, long long* trace, cudaStream_t st) {
   if (rows == 0) return LIST_OK;
   LIST_CHECK_ARG(w->n0 == tc::N0 && w->n1 == tc::N1 && w->n2 == tc::N2,
                  "mlp_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
@@ -471,6 +495,7 @@ int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, in
   aa.addend = xh;
   aa.ld = ldx;
   aa.k = k;
+  aa.trace = trace;
   const tc::ProjArgs none;
   if (variant == 3) return tc::launch<2, 3>(&wv, xh + tc::N0, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, aa, st);
   return tc::launch<2, 4>(&wv, xh + tc::N0, ldx, rows, sdf, out_div, dbg1, dbg2, dbg3, none, aa, st);
