@@ -27,24 +27,37 @@ namespace tc {
 constexpr int BM = 128;                 // rows per CTA
 constexpr int BK = 64;                  // bf16 elements per K chunk = 128 B = one swizzle atom row
 constexpr int N0 = 512, N1 = 256, N2 = 256;
-constexpr int A_BYTES = BM * BK * 2;    // 16 KB
-constexpr int SUB_BYTES = 128 * BK * 2; // one 128-row weight box, 16 KB
+constexpr int UNIT_BYTES = 128 * BK * 2; // one 128-row x 64-column box (X, weight or addend), 16 KB
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
+constexpr int NA = N0 / BK;             // addend boxes per tile (hoisted rows)
 
 template <int CG, int ST>
 struct Cfg {
   static constexpr int SUBS_L0 = (N0 / 128) / CG;     // weight boxes per CTA per fc_0 chunk
   static constexpr int SUBS_L12 = (N1 / 128) / CG;    // per fc_1 / fc_2 chunk
-  static constexpr int STAGE_BYTES = A_BYTES + SUBS_L0 * SUB_BYTES;
-  static constexpr int STAGES = ST;
-  static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int U0 = 1 + SUBS_L0;              // units of one fc_0 chunk (X box + weight boxes)
+  static constexpr int NU = ST * U0;                  // ring units (ST fc_0 chunks deep)
+  static constexpr int NB = NU;                       // chunk barriers (a chunk has >= 1 unit)
+  static constexpr int RING_BYTES = NU * UNIT_BYTES;
   static constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;   // b0 b1 b2 w3
   static constexpr int BAR_OFF = RING_BYTES + PARAM_FLOATS * 4;
-  static constexpr int SMEM_BYTES = BAR_OFF + (2 * STAGES + 2) * 8 + 16 + 1024 /*align slack*/;
+  static constexpr int NUM_BARS = 2 * NB + NA + 2;    // full[NB] empty[NB] afull[NA] dfull hready
+  static constexpr int SMEM_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024 /*align slack*/;
 };
 
 // ------------------------------------------------------------------ kernel
+// Operand ring.  Shared memory holds NU units of 16 KB; operands travel as CHUNKS of 1..U0 consecutive units
+// (wrapping), allocated first-in first-out by the TMA producer:
+//     fc_0 chunk kc : [X box | weight boxes]                      -> consumed by the MMA thread
+//     addend box a  : 64 columns of the hoisted rows' addend block -> consumed by the epilogue warps (hoisted rows only)
+//     fc_1 / fc_2   : weight boxes                                 -> consumed by the MMA thread
+// in exactly that order per tile.  Chunk number q (counted over the whole kernel) owns barriers full[q % NB] (leader
+// CTA; MMA-consumed chunks only), afull[a] (local; addend boxes) and empty[q % NB] (local in every CTA: completed by the
+// multicast tcgen05.commit for MMA-consumed chunks, by an elected epilogue thread for addend boxes), so the empty phase
+// of chunk q is q / NB everywhere.  Because the addend boxes and ALL of W1 / W2 fit in the ring at once (8 + 8 + 4 units
+// of 12), the producer fetches them while fc_0 and the first epilogue run: the epilogue reads the addend from shared
+// memory and fc_1 / fc_2 never wait for a weight tile.
 template <int CG, int ST>
 __global__ void __launch_bounds__(kThreads, 1)
 mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
@@ -53,8 +66,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
               const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ sdf,
               long long rows, int nk0, float out_div, float* __restrict__ dbg1, float* __restrict__ dbg2,
               float* __restrict__ dbg3, __nv_bfloat16* __restrict__ proj_out, int proj_groups, int proj_w_col_stride,
-              long long proj_out_group_stride, const __nv_bfloat16* __restrict__ addend, long long ld_add,
-              long long* __restrict__ trace) {
+              long long proj_out_group_stride, int xcol0, int has_add, long long* __restrict__ trace) {
   using C = Cfg<CG, ST>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -66,12 +78,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   float* const s_b2 = s_b1 + N1;
   float* const s_w3 = s_b2 + N2;
   const uint32_t bar0 = base + C::BAR_OFF;
-  auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (C::STAGES + s); };
-  const uint32_t dfull_bar = bar0 + 8u * (2 * C::STAGES);
+  auto full_bar = [&](uint32_t b) { return bar0 + 8u * b; };
+  auto empty_bar = [&](uint32_t b) { return bar0 + 8u * (C::NB + b); };
+  auto afull_bar = [&](uint32_t a) { return bar0 + 8u * (2 * C::NB + a); };
+  const uint32_t dfull_bar = bar0 + 8u * (2 * C::NB + NA);
   const uint32_t hready_bar = dfull_bar + 8u;
   const uint32_t tmem_slot = hready_bar + 8u;
-  volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + C::BAR_OFF + (2 * C::STAGES + 2) * 8);
+  volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + C::BAR_OFF + C::NUM_BARS * 8);
+  auto unit_addr = [&](uint32_t u) { return base + (u % C::NU) * UNIT_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = (CG == 2) ? cluster_ctarank() : 0u;
@@ -83,8 +97,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   // column blocks of W0 (block g starts at column g * proj_w_col_stride): every group multiplies the same
   // X rows and writes its own [rows][512] output slab.
   const bool proj = proj_out != nullptr;
+  const bool add = has_add != 0;          // hoisted rows: columns [0, N0) of the X map are the addend block, fc_0's K starts at xcol0
   const int tiles_per_group = static_cast<int>((rows + rows_per_tile - 1) / rows_per_tile);
   const int num_tiles = proj ? tiles_per_group * proj_groups : tiles_per_group;
+  // chunk sequence of one tile
+  const int n_add = add ? NA : 0;
+  const int n_l12 = proj ? 0 : (N0 + N1) / BK;                       // 8 fc_1 + 4 fc_2 weight chunks
+  const int chunks_per_tile = nk0 + n_add + n_l12;
+  const int units_per_tile = nk0 * C::U0 + n_add + n_l12 * C::SUBS_L12;
+  auto units_of = [&](int i) { return i < nk0 ? C::U0 : (i < nk0 + n_add ? 1 : C::SUBS_L12); };
 
   // Diagnostic phase timeline (list_mlp_hoisted_trace): CTA 0 stamps clock64() at the phase boundaries of its first
   // kTraceTiles tiles: slots 0..5 by the MMA thread (tile start, fc_0 issued, fc_1 start, fc_1 issued, fc_2 start,
@@ -100,10 +121,11 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     tma_prefetch_desc(&tmW0);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+    for (int b = 0; b < C::NB; ++b) {
+      mbar_init(full_bar(b), 1);
+      mbar_init(empty_bar(b), 1);
     }
+    for (int a = 0; a < NA; ++a) mbar_init(afull_bar(a), 1);
     mbar_init(dfull_bar, 1);
     mbar_init(hready_bar, 128 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -124,44 +146,54 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const uint32_t stage0 = base;
-  auto stage_a = [&](int s) { return stage0 + static_cast<uint32_t>(s) * C::STAGE_BYTES; };
-  auto stage_b = [&](int s) { return stage0 + static_cast<uint32_t>(s) * C::STAGE_BYTES + A_BYTES; };
-
   if (warp == 0) {
     // =========================== TMA producer ===========================
     if (lane == 0) {
-      uint32_t slot = 0;
+      uint32_t q = 0, head = 0;                 // next chunk number / first free unit
+      uint32_t tail_q = 0;                      // oldest chunk whose units are not known to be free yet
+      int tail_i = 0, free_units = C::NU;
+      auto make_room = [&](int n) {
+        while (free_units < n) {
+          mbar_wait(empty_bar(tail_q % C::NB), (tail_q / C::NB) & 1);
+          free_units += units_of(tail_i);
+          if (++tail_i == chunks_per_tile) tail_i = 0;
+          ++tail_q;
+        }
+        free_units -= n;
+      };
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
         const int group = tile / tiles_per_group;
         const int row0 = static_cast<int>((tile - group * tiles_per_group) * rows_per_tile + rank * BM);
         const int wcol0 = group * proj_w_col_stride;
-        for (int kc = 0; kc < nk0; ++kc, ++slot) {                    // fc_0: X chunk + W0 chunk
-          const int s = slot % C::STAGES;
-          mbar_wait(empty_bar(s), ((slot / C::STAGES) & 1) ^ 1);
-          const uint32_t fb = (CG == 2) ? mapa(full_bar(s), 0) : full_bar(s);
-          if (rank == 0) mbar_expect_tx(full_bar(s), CG * C::STAGE_BYTES);
-          tma_load_2d<CG>(&tmX, fb, stage_a(s), kc * BK, row0);
+        for (int kc = 0; kc < nk0; ++kc, ++q, head += C::U0) {            // fc_0: X box + W0 boxes
+          make_room(C::U0);
+          const uint32_t fb = (CG == 2) ? mapa(full_bar(q % C::NB), 0) : full_bar(q % C::NB);
+          if (rank == 0) mbar_expect_tx(full_bar(q % C::NB), CG * C::U0 * UNIT_BYTES);
+          tma_load_2d<CG>(&tmX, fb, unit_addr(head), xcol0 + kc * BK, row0);
 #pragma unroll
           for (int j = 0; j < C::SUBS_L0; ++j) {
             const int wrow = (CG == 1) ? j * 128 : j * 256 + static_cast<int>(rank) * 128;
-            tma_load_2d<CG>(&tmW0, fb, stage_b(s) + j * SUB_BYTES, wcol0 + kc * BK, wrow);
+            tma_load_2d<CG>(&tmW0, fb, unit_addr(head + 1 + j), wcol0 + kc * BK, wrow);
           }
+        }
+        for (int a = 0; a < n_add; ++a, ++q, ++head) {                      // addend boxes: this CTA's rows, local barrier
+          make_room(1);
+          mbar_expect_tx(afull_bar(a), UNIT_BYTES);
+          tma_load_2d<1>(&tmX, afull_bar(a), unit_addr(head), a * BK, row0);
         }
         if (proj) continue;
 #pragma unroll 1
-        for (int layer = 1; layer <= 2; ++layer) {                    // fc_1 / fc_2: weights only
+        for (int layer = 1; layer <= 2; ++layer) {                          // fc_1 / fc_2: weights only
           const CUtensorMap* tm = (layer == 1) ? &tmW1 : &tmW2;
           const int nk = (layer == 1 ? N0 : N1) / BK;
-          for (int kc = 0; kc < nk; ++kc, ++slot) {
-            const int s = slot % C::STAGES;
-            mbar_wait(empty_bar(s), ((slot / C::STAGES) & 1) ^ 1);
-            const uint32_t fb = (CG == 2) ? mapa(full_bar(s), 0) : full_bar(s);
-            if (rank == 0) mbar_expect_tx(full_bar(s), CG * C::SUBS_L12 * SUB_BYTES);
+          for (int kc = 0; kc < nk; ++kc, ++q, head += C::SUBS_L12) {
+            make_room(C::SUBS_L12);
+            const uint32_t fb = (CG == 2) ? mapa(full_bar(q % C::NB), 0) : full_bar(q % C::NB);
+            if (rank == 0) mbar_expect_tx(full_bar(q % C::NB), CG * C::SUBS_L12 * UNIT_BYTES);
 #pragma unroll
             for (int j = 0; j < C::SUBS_L12; ++j) {
               const int wrow = (CG == 1) ? j * 128 : static_cast<int>(rank) * 128;
-              tma_load_2d<CG>(tm, fb, stage_b(s) + j * SUB_BYTES, kc * BK, wrow);
+              tma_load_2d<CG>(tm, fb, unit_addr(head + j), kc * BK, wrow);
             }
           }
         }
@@ -170,9 +202,17 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
   } else if (warp == 1) {
     // =========================== MMA issuer (leader CTA, one thread) ===========================
     if (rank == 0 && lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(128 * CG, 256);
-      constexpr uint32_t kInstrB = (256 / CG) * BK * 2;             // bytes of B one N=256 instruction reads per CTA
-      uint32_t slot = 0, hphase = 0;
+      // one instruction covers 128*CG accumulator columns: weight box j of every CTA of the group
+      constexpr uint32_t idesc = umma_idesc(128 * CG, 128 * CG);
+      constexpr uint32_t kCols = 128 * CG;
+      uint32_t q = 0, head = 0, hphase = 0;
+      uint32_t fphase = 0;                                            // bit b: parity the next wait on full[b] expects
+      auto wait_full = [&]() {
+        const uint32_t b = q % C::NB;
+        mbar_wait(full_bar(b), (fphase >> b) & 1u);
+        fphase ^= 1u << b;
+        tc_fence_after();
+      };
       bool first = true;
       int tno = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++tno) {
@@ -181,24 +221,24 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         tc_fence_after();
         stamp(tno, 0);
         // ---- fc_0: D[0,512) = X · W0^T ----
-        for (int kc = 0; kc < nk0; ++kc, ++slot) {
-          const int s = slot % C::STAGES;
-          mbar_wait(full_bar(s), (slot / C::STAGES) & 1);
-          tc_fence_after();
-          const uint64_t ad = umma_desc_sw128(stage_a(s));
-          const uint64_t bd = umma_desc_sw128(stage_b(s));
+        for (int kc = 0; kc < nk0; ++kc, head += C::U0) {
+          wait_full();
+          const uint64_t ad = umma_desc_sw128(unit_addr(head));
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              umma_ss<CG>(tmem_base + i * 256, ad + 2 * k, bd + ((i * kInstrB) >> 4) + 2 * k, idesc,
+            for (int j = 0; j < C::SUBS_L0; ++j) {
+              umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k, umma_desc_sw128(unit_addr(head + 1 + j)) + 2 * k, idesc,
                           (kc | k) != 0 ? 1u : 0u);
             }
           }
-          umma_commit<CG>(empty_bar(s));
+          umma_commit<CG>(empty_bar(q % C::NB));
+          ++q;
         }
         umma_commit<CG>(dfull_bar);
         stamp(tno, 1);
+        q += n_add;                                                     // addend boxes belong to the epilogue
+        head += n_add;
         if (proj) continue;
         // ---- fc_1: D[256,512) = H1(TMEM [0,256)) · W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) · W2^T ----
 #pragma unroll 1
@@ -207,18 +247,19 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           mbar_wait(hready_bar, hphase); hphase ^= 1;
           tc_fence_after();
           stamp(tno, 2 * layer);
-          for (int kc = 0; kc < nk; ++kc, ++slot) {
-            const int s = slot % C::STAGES;
-            mbar_wait(full_bar(s), (slot / C::STAGES) & 1);
-            tc_fence_after();
-            const uint64_t bd = umma_desc_sw128(stage_b(s));
+          for (int kc = 0; kc < nk; ++kc, head += C::SUBS_L12) {
+            wait_full();
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
-              // A operand: 16 bf16 of K = 8 TMEM columns
-              umma_ts<CG>(tmem_base + 256, tmem_base + kc * (BK / 2) + k * 8, bd + 2 * k, idesc,
-                          (kc | k) != 0 ? 1u : 0u);
+#pragma unroll
+              for (int j = 0; j < C::SUBS_L12; ++j) {
+                // A operand: 16 bf16 of K = 8 TMEM columns
+                umma_ts<CG>(tmem_base + 256 + j * kCols, tmem_base + kc * (BK / 2) + k * 8,
+                            umma_desc_sw128(unit_addr(head + j)) + 2 * k, idesc, (kc | k) != 0 ? 1u : 0u);
+              }
             }
-            umma_commit<CG>(empty_bar(s));
+            umma_commit<CG>(empty_bar(q % C::NB));
+            ++q;
           }
           umma_commit<CG>(dfull_bar);
           stamp(tno, 2 * layer + 1);
@@ -231,19 +272,14 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t hready_remote = (CG == 2) ? mapa(hready_bar, 0) : hready_bar;
     const float bias3 = __ldg(b3);
+    const int r_in_tile = quarter * 32 + lane;                         // row of the CTA's 128-row tile
     uint32_t dphase = 0;
     int etno = 0;
     const bool estamp = warp == kEpiWarp0 && lane == 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++etno) {
       const int group = tile / tiles_per_group;
-      const long long row = (tile - group * tiles_per_group) * rows_per_tile + rank * BM + quarter * 32 + lane;
+      const long long row = (tile - group * tiles_per_group) * rows_per_tile + rank * BM + r_in_tile;
       // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
-      if (addend != nullptr) {                               // the epilogue is idle while fc_0 runs: pull the row's addend into L2
-        const __nv_bfloat16* const arow = addend + (row < rows ? row : rows - 1) * ld_add;
-#pragma unroll
-        for (int i = 0; i < (N0 * 2) / 128; ++i)
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(arow) + i * 128));
-      }
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(etno, 6);
@@ -270,49 +306,47 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
         else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
         continue;
       }
-      if (addend != nullptr) {
-        // Hoisted rows (hoist.cu): fc_0's accumulator covers only the non-hoisted K columns; the 512-wide addend
-        // block of the row (projected maps / coarse levels + bias b0, bf16) is added here.  The row was prefetched
-        // into L2 before the dfull wait; two 32-column chunks are kept in flight in registers.
-        const __nv_bfloat16* const arow = addend + (row < rows ? row : rows - 1) * ld_add;
-#ifndef LIST_MLP_ADD_DEPTH
-#define LIST_MLP_ADD_DEPTH 2
-#endif
-        constexpr int kDepth = LIST_MLP_ADD_DEPTH;          // 32-column chunks of the addend kept in flight
-        uint4 pq[kDepth][4];
+      if (add) {
+        // Hoisted rows (hoist.cu): fc_0's accumulator covers only the non-hoisted K columns; the 512-wide addend block of
+        // the rows (projected maps / coarse levels + bias b0, bf16) arrived by TMA in NA boxes of 64 columns (128-byte
+        // swizzle: row r at r*128, 16-byte slot s at (s ^ (r & 7)) * 16 -- conflict free for consecutive rows).
+        const uint32_t q_add0 = static_cast<uint32_t>(etno) * chunks_per_tile + nk0;
+        const uint32_t head_add0 = static_cast<uint32_t>((static_cast<long long>(etno) * units_per_tile + nk0 * C::U0) % C::NU);
+#pragma unroll 1
+        for (int a = 0; a < NA; ++a) {
+          mbar_wait_warp(afull_bar(a), etno & 1);
+          const uint32_t urow = unit_addr(head_add0 + a) + r_in_tile * 128;
 #pragma unroll
-        for (int d = 0; d < kDepth; ++d)
+          for (int h = 0; h < 2; ++h) {
+            const int j = 2 * a + h;
+            uint32_t v[32], u[16];
+            uint4 pq[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) pq[d][i] = __ldg(reinterpret_cast<const uint4*>(arow + d * 32) + i);
-        auto chunk = [&](int j, uint4 (&pq)[4]) {
-          uint32_t v[32], u[16];
-          tmem_ld32(tq + j * 32, v);
+            for (int i = 0; i < 4; ++i)
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(pq[i].x), "=r"(pq[i].y), "=r"(pq[i].z), "=r"(pq[i].w)
+                           : "r"(urow + (((4 * h + i) ^ (r_in_tile & 7)) << 4)) : "memory");
+            tmem_ld32(tq + j * 32, v);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const uint32_t w4[4] = {pq[i].x, pq[i].y, pq[i].z, pq[i].w};
+            for (int i = 0; i < 4; ++i) {
+              const uint32_t w4[4] = {pq[i].x, pq[i].y, pq[i].z, pq[i].w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[8 * i + 2 * e] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e]) + __uint_as_float(w4[e] << 16), 0.f));
-              v[8 * i + 2 * e + 1] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e + 1]) + __uint_as_float(w4[e] & 0xffff0000u), 0.f));
+              for (int e = 0; e < 4; ++e) {
+                v[8 * i + 2 * e] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e]) + __uint_as_float(w4[e] << 16), 0.f));
+                v[8 * i + 2 * e + 1] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e + 1]) + __uint_as_float(w4[e] & 0xffff0000u), 0.f));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) u[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+            tmem_st16(tq + j * 16, u);
+            if (dbg1 != nullptr && row < rows) {
+              float* const drow = dbg1 + row * N0 + j * 32;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) drow[i] = __uint_as_float(v[i]);
             }
           }
-          if (j + kDepth < N0 / 32) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) pq[i] = __ldg(reinterpret_cast<const uint4*>(arow + (j + kDepth) * 32) + i);
-          }
-#pragma unroll
-          for (int i = 0; i < 16; ++i) u[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-          tmem_st16(tq + j * 16, u);
-          if (dbg1 != nullptr && row < rows) {
-            float* const drow = dbg1 + row * N0 + j * 32;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) drow[i] = __uint_as_float(v[i]);
-          }
-        };
-#pragma unroll 1
-        for (int j = 0; j < N0 / 32; j += kDepth) {
-#pragma unroll
-          for (int d = 0; d < kDepth; ++d) chunk(j + d, pq[d]);
+          named_bar_sync(1, 128);                            // all four epilogue warps are done with the box ...
+          if (threadIdx.x == kEpiWarp0 * 32) mbar_arrive_local(empty_bar((q_add0 + a) % C::NB));   // ... hand its unit back
         }
       } else {
 #pragma unroll 1
@@ -422,7 +456,11 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   const bool proj = pa.out != nullptr;
   const int k0 = proj ? pa.k : (aa.k > 0 ? aa.k : w->k_pad);
   const uint64_t w0_cols = proj ? static_cast<uint64_t>(pa.w_col_stride) * (pa.groups - 1) + pa.k : k0;
-  if ((rc = make_map_bf16(&tmX, X, k0, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx)))) return rc;
+  // hoisted rows: ONE map over [addend N0 | k0 columns]; fc_0's chunks start at column N0, the addend boxes at 0
+  const bool hoisted = aa.addend != nullptr;
+  const void* xbase = hoisted ? static_cast<const void*>(aa.addend) : X;
+  const uint64_t xcols = hoisted ? static_cast<uint64_t>(N0) + k0 : static_cast<uint64_t>(k0);
+  if ((rc = make_map_bf16(&tmX, xbase, xcols, static_cast<uint64_t>(rows), static_cast<uint64_t>(ldx)))) return rc;
   if ((rc = make_map_bf16(&tmW0, w->w0, w0_cols, N0, w->k_pad))) return rc;
   if ((rc = make_map_bf16(&tmW1, w->w1, N0, N1, N0))) return rc;
   if ((rc = make_map_bf16(&tmW2, w->w2, N1, N2, N1))) return rc;
@@ -451,7 +489,7 @@ static int launch(const ListWeights* w, const void* X, int64_t ldx, int64_t rows
   const int nk0 = k0 / BK;
   LIST_CUDA(cudaLaunchKernelEx(&cfg, mlp_tc_kernel<CG, ST>, tmX, tmW0, tmW1, tmW2, w->b0, w->b1, w->b2, w->w3, w->b3,
                                sdf, static_cast<long long>(rows), nk0, out_div, dbg1, dbg2, dbg3, pa.out, pa.groups,
-                               pa.w_col_stride, static_cast<long long>(rows) * N0, aa.addend, static_cast<long long>(aa.ld), aa.trace));
+                               pa.w_col_stride, static_cast<long long>(rows) * N0, hoisted ? N0 : 0, hoisted ? 1 : 0, aa.trace));
   return LIST_OK;
 }
 
