@@ -3,12 +3,13 @@
 // as ONE persistent warp-specialised sm_100a kernel.  Per CTA a 128-row tile of X runs through
 // all four layers without leaving the SM:
 //
-//   TMA (cp.async.bulk.tensor, 128B swizzle) streams X[128 x 64] and weight[128 x 64] boxes into
-//   a shared-memory ring;  tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulates in TMEM;
+//   TMA (cp.async.bulk.tensor, 128B swizzle) streams 16 KB boxes (128 rows x 64 columns of X, of a weight matrix, or
+//   of the hoisted rows' addend block) into a shared-memory ring of 12 units managed as a chunk FIFO (see the kernel);
+//   tcgen05.mma (kind::f16, bf16 x bf16 -> fp32) accumulates in TMEM;
 //   fc_0's 128x512 fp32 accumulator fills all 512 TMEM columns;  the epilogue warps read it with
-//   tcgen05.ld, add bias, ReLU, round to bf16 and write it BACK to TMEM (tcgen05.st) as the
-//   A operand of fc_1 (A-from-TMEM MMA), likewise for fc_2;  fc_out (256 -> 1) is a register dot
-//   product in the last epilogue.  The feature concat was already done by the gather kernel's
+//   tcgen05.ld, add bias (or, on hoisted rows, the addend block read from the ring), ReLU, round to bf16 and write it
+//   BACK to TMEM (tcgen05.st) as the A operand of fc_1 (A-from-TMEM MMA), likewise for fc_2;  fc_out (256 -> 1) is a
+//   register dot product in the last epilogue.  The feature concat was already done by the gather kernel's
 //   row layout, biases / activations / the final /sdf_scale are fused here.
 //
 //   TMEM columns : fc_0 acc [0,512) -> H1 bf16 [0,256) -> fc_1 acc [256,512) -> H2 bf16 [0,128)
@@ -17,8 +18,9 @@
 //                  warps 2..5 = epilogue (one TMEM lane quarter each).
 //   CG = 2       : a CTA pair (cluster 2x1x1) runs tcgen05.mma.cta_group::2 (M = 256): each CTA
 //                  loads its own 128 rows of X and HALF of every weight tile, which halves the
-//                  L2 -> SM weight traffic per row -- the real bound of this kernel, since W0
-//                  (3.7 MB) is re-streamed for every row tile.
+//                  L2 -> SM weight traffic per row, since W0 is re-streamed for every row tile.
+//   Measured per 128-row tile on hoisted rows (K = 832; list_mlp_hoisted_trace, profiles/r01_mlp_phase_trace.txt):
+//   fc_0 7.5 us | ep0 3.9 | fc_1 2.6 | ep1 1.3 | fc_2 1.5 | ep2 1.2 | three hand-offs 2.1  = 20.0 us, 58 % of it MMA.
 #include "tc_common.cuh"
 
 namespace list {
