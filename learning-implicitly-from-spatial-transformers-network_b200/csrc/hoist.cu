@@ -72,7 +72,11 @@ __device__ __forceinline__ float step_q0(const TileMap& m, const TileSpan& t, in
   return linspace_f32(static_cast<int>(t.g_tile0 % m.res) + s, m.res, m.bb_min, m.bb_max) * 2.0f;
 }
 
-constexpr int kTile = 128;          // max steps per tile
+constexpr int kTile = 128;          // max steps per tile (rest kernel)
+#ifndef LIST_ADD_TILE
+#define LIST_ADD_TILE 128
+#endif
+constexpr int kAddTile = LIST_ADD_TILE;   // steps per tile of the addend kernel (multiple of 128)
 constexpr int kN0 = 512;            // fc_0 width == addend channels
 constexpr int kRestThreads = 256;
 constexpr int kRestLevels = 4;      // non-hoisted levels (vector ones first)
@@ -186,18 +190,18 @@ template <int V>
 __global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_kernel(const AddParams p) {
   constexpr int NT = kN0 / V;
   constexpr int NC = kMaxH * 3;
-  __shared__ __align__(16) float s_w[kTile][12];        // per step: w0 of the 6 classes, w00 w01 w10 w11, 2 pad
-  __shared__ int s_i0[NC][kTile];
-  __shared__ int s_xy[kTile];                           // y0 << 16 | x0
-  __shared__ uint32_t s_ctl[kTile];
-  __shared__ uint32_t s_any[kTile / 32];
+  __shared__ __align__(16) float s_w[kAddTile][12];        // per step: w0 of the 6 classes, w00 w01 w10 w11, 2 pad
+  __shared__ int s_i0[NC][kAddTile];
+  __shared__ int s_xy[kAddTile];                           // y0 << 16 | x0
+  __shared__ uint32_t s_ctl[kAddTile];
+  __shared__ uint32_t s_any[kAddTile / 32];
   __shared__ Corner s_corner[kMaxH][LIST_NUM_DISP * 4];
   const int tid = threadIdx.x;
   TileSpan t;
   if (!tile_span(p.tm, blockIdx.x, t)) return;
 
   // ---- phase 0a: per step 2-D cell / weights and voxel index / weight of every class ----
-  for (int s = tid; s < kTile; s += NT) {
+  for (int s = tid; s < kAddTile; s += NT) {
     int x0 = 0, y0 = 0;
     float w00 = 0.f, w01 = 0.f, w10 = 0.f, w11 = 0.f;                    // NaN grid -> all taps out of bounds
     float q[3] = {0.f, t.qy, t.qz};
@@ -243,9 +247,9 @@ __global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_k
   }
   __syncthreads();
   // ---- phase 0b: control words ----
-  uint32_t myctl[kTile / NT];
+  uint32_t myctl[kAddTile / NT];
 #pragma unroll
-  for (int it = 0; it < kTile / NT; ++it) {
+  for (int it = 0; it < kAddTile / NT; ++it) {
     const int s = tid + it * NT;
     uint32_t ctl = 0;
     if (s >= t.s_lo && s < t.s_hi) {
@@ -261,17 +265,17 @@ __global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_k
   }
   __syncthreads();
 #pragma unroll
-  for (int it = 0; it < kTile / NT; ++it) {
+  for (int it = 0; it < kAddTile / NT; ++it) {
     const int s = tid + it * NT;
-    int nxt = kTile - s;                                                 // steps to the next break (clipped to s_hi later)
+    int nxt = kAddTile - s;                                                 // steps to the next break (clipped to s_hi later)
     const int w = s >> 5, bit = s & 31;
     const uint32_t rest = bit == 31 ? 0u : (s_any[w] >> (bit + 1));
     if (rest) nxt = __ffs(rest);
     else {
-      for (int w2 = w + 1; w2 < kTile / 32; ++w2)
+      for (int w2 = w + 1; w2 < kAddTile / 32; ++w2)
         if (s_any[w2]) { nxt = w2 * 32 + __ffs(s_any[w2]) - 1 - s; break; }
     }
-    s_ctl[s] = myctl[it] | (static_cast<uint32_t>(nxt) << 8);
+    s_ctl[s] = myctl[it] | (static_cast<uint32_t>(nxt) << 8);       // distance < 2^16
   }
   __syncthreads();
 
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_k
       loadv<V>(pm + (static_cast<size_t>(y1) * p.S + cx) * kN0, v10);
       loadv<V>(pm + (static_cast<size_t>(y1) * p.S + x1) * kN0, v11);
     }
-    const int n = min(static_cast<int>((ctl >> 8) & 0xffu), t.s_hi - s);
+    const int n = min(static_cast<int>((ctl >> 8) & 0xffffu), t.s_hi - s);
 #pragma unroll 2
     for (int k = 0; k < n; ++k, ++s, dst += p.ldx) {
       const float4 wa = *reinterpret_cast<const float4*>(&s_w[s][0]);
@@ -764,7 +768,7 @@ int gather(const ListCtx* ctx, const ListWeights* w, const Plan& pl, const void*
   a.X = static_cast<__nv_bfloat16*>(X);
   a.ldx = ldx;
   a.S = ctx->map_size;
-  fill_tilemap(&a.tm, res, bb_min, bb_max, begin, count, kTile);
+  fill_tilemap(&a.tm, res, bb_min, bb_max, begin, count, kAddTile);
 
   RestParams r{};
   size_t smem = 0;

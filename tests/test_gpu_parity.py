@@ -347,6 +347,22 @@ def test_hoisted_rows_addend_and_verbatim_columns():
     assert torch.equal(a + b, hs.gather_grid(0, 32, 100, 1000))
 
 
+@pytest.mark.parametrize("res,begin,count", [(5, 0, 125), (5, 7, 60), (130, 130 * 130 * 64 + 77, 5000), (300, 300 * 300 * 150 + 299, 4000),
+                                             (256, 256 * 256 * 200 + 100, 700)])
+def test_hoisted_path_on_awkward_grid_sizes(res, begin, count, monkeypatch):
+    """z-lines shorter than a tile, longer than two tiles, ranges starting / ending inside a z-line: the hoisted
+    dense-grid path against the un-hoisted one on the same points (both bf16 evaluations of the same values)."""
+    inp = synth.make_inputs(seed=23, B=1, N=8, size="small", trans="camera")
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "bf16")
+    a = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=1024)
+    whole = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=count)
+    assert torch.equal(a, whole)                             # chunking never changes a value
+    monkeypatch.setenv("LIST_B200_HOIST", "0")
+    b = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=1024)
+    assert torch.isfinite(a).all() and (a - b).abs().max().item() <= 2e-3
+
+
 def test_hoisted_grid_sdf_vs_oracle_and_unhoisted(monkeypatch):
     inp = synth.make_inputs(seed=22, B=1, N=8, size="small", trans="camera")
     ref = P.dense_grid_sdf(inp.maps, inp.vols, inp.trans_mat, inp.weights, 32, sdf_scale=10.0, chunk=8192).reshape(-1)
