@@ -374,3 +374,26 @@ def test_hoisted_grid_sdf_vs_oracle_and_unhoisted(monkeypatch):
     e_h, e_p = np.abs(hoisted - ref).max(), np.abs(plain - ref).max()
     print(f"bf16 grid 32^3 vs oracle: hoisted {e_h:.3e}, unhoisted {e_p:.3e} (sdf/10)")
     assert e_h <= BF16_TOL and e_p <= BF16_TOL
+
+
+def test_host_buffer_entry_points_equal_the_resident_path():
+    """list_sdf_grid_host (C ABI, host pointers) and parallel.ShardedHostRunner (bench.py's e2e leg) against
+    hotpath.grid_sdf on device-resident tensors: bit-identical SDF values."""
+    from list_b200 import parallel
+    inp = synth.make_inputs(seed=41, B=1, N=8, size="small", trans="camera")
+    g = inp.to(DEV)
+    res, begin, count = 48, 48 * 48 * 3, 48 * 48 * 20
+    for mode in ("bf16", "fp32"):
+        ctx, kw = ctx_and_weights(g, mode)
+        want = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=8192)
+        pin = lambda t: t.contiguous().pin_memory()
+        maps, vols, T = [pin(m) for m in inp.maps], [pin(v) for v in inp.vols], pin(inp.trans_mat)
+        c_path = hotpath.HostGridRunner(maps, vols, T, kw, res, begin, count, mode, 8192).run(10.0)
+        torch.cuda.synchronize()
+        assert torch.equal(c_path, want.cpu()), mode
+        if mode == "bf16":
+            runner = parallel.ShardedHostRunner(maps, vols, T, kw, res, mode, 8192)      # single rank: the whole grid
+            out = runner.run(10.0)
+            torch.cuda.synchronize()
+            whole = hotpath.grid_sdf(ctx, kw, res, 0, res ** 3, sdf_scale=10.0, chunk_rows=8192)
+            assert torch.equal(out, whole.cpu())
