@@ -397,3 +397,44 @@ def test_host_buffer_entry_points_equal_the_resident_path():
             torch.cuda.synchronize()
             whole = hotpath.grid_sdf(ctx, kw, res, 0, res ** 3, sdf_scale=10.0, chunk_rows=8192)
             assert torch.equal(out, whole.cpu())
+
+
+# ------------------------------------------------------------------ SURVEY.md §8d parity gates at the configured sizes
+def _camera_inputs():
+    return synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")
+
+
+def test_parity_gate_cfg1_full_64_cubed_grid():
+    """cfg-1: every point of the 64^3 grid over the full-size per-image tensors, against the ATen-op oracle on the
+    CPU: fp32 <= 1e-4 with the same sign at every vertex (up to |sdf| <= 1e-4), bf16 <= 2e-2 (network units)."""
+    inp = _camera_inputs()
+    ref = P.dense_grid_sdf(inp.maps, inp.vols, inp.trans_mat, inp.weights, 64, sdf_scale=1.0)          # (64,64,64)
+    g = inp.to(DEV)
+    out = {}
+    for mode in ("fp32", "bf16"):
+        ctx, kw = ctx_and_weights(g, mode)
+        out[mode] = hotpath.grid_sdf(ctx, kw, 64, sdf_scale=1.0, chunk_rows=65536)[0].view(64, 64, 64).cpu().numpy()
+    e32, e16 = np.abs(out["fp32"] - ref), np.abs(out["bf16"] - ref)
+    flipped = np.sign(out["fp32"]) != np.sign(ref)
+    print(f"cfg-1 64^3: fp32 max|dSDF| {e32.max():.2e}, bf16 max {e16.max():.2e} (median {np.median(e16):.1e}), "
+          f"flipped vertices {int(flipped.sum())}, MC cells changed {int((O.mc_case_index(out['fp32']) != O.mc_case_index(ref)).sum())}")
+    assert e32.max() <= FP32_TOL and e16.max() <= BF16_TOL
+    assert np.all(np.abs(ref[flipped]) <= FP32_TOL)
+
+
+def test_parity_gate_cfg4_strided_subsample_of_256_cubed():
+    """cfg-4: the whole 256^3 grid is evaluated on the GPU (bf16 production path and fp32 parity path); every 64th
+    point (262 144 of them) is checked against the oracle on the CPU."""
+    inp = _camera_inputs()
+    res, stride = 256, 64
+    g = inp.to(DEV)
+    idx = torch.arange(5, res ** 3, stride)
+    pts = hotpath.grid_points(res).cpu()[idx].unsqueeze(0)
+    with torch.no_grad():
+        ref = torch.cat([P.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights) for p in torch.split(pts, 65536, 1)], 1)[0] / 10.0
+    for mode, tol in (("bf16", BF16_TOL / 10.0), ("fp32", FP32_TOL / 10.0)):          # values are SDF / sdf_scale
+        ctx, kw = ctx_and_weights(g, mode)
+        full = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=1048576 if mode == "bf16" else 131072)[0]
+        err = (full.cpu()[idx] - ref).abs()
+        print(f"cfg-4 256^3 subsample, {mode}: max|dSDF|/scale {err.max().item():.2e} over {idx.numel()} points")
+        assert err.max().item() <= tol
