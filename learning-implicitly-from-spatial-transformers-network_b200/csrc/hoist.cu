@@ -104,6 +104,7 @@ struct RestParams {
   int cells_max[kRestLevels];       // table rows per (level, displacement)
   int toff[kRestLevels];            // first float of the level's tables in shared memory
   int nvl, nsl;                     // vector levels [0, nvl), scalar levels [nvl, nvl + nsl)
+  int lwarp0[kRestLevels + 1];      // phase L: warps [lwarp0[i], lwarp0[i+1]) work on vector level i
   int nvec;                         // 16-byte items per row of the vector levels
   int g_items;                      // phase-G items of the vector levels
   int tail0, xyz_off, k_h;          // tail region [tail0, k_h): scalar levels, q, zero pad
@@ -113,6 +114,7 @@ struct RestParams {
 };
 
 __device__ __forceinline__ int shift_class(int d) { return d == 1 ? 1 : (d == 2 ? 2 : 0); }
+__device__ __forceinline__ int warp_of(int tid) { return tid >> 5; }
 __device__ __forceinline__ float class_shift(int cls) { return cls == 0 ? 0.f : (cls == 1 ? -kDisplacement : kDisplacement); }
 // floor(a / b) for 0 <= a < 2^20, 1 <= b < 2^10 through the float reciprocal (exact in that range)
 __device__ __forceinline__ int fast_div(int a, float inv_b) { return static_cast<int>((static_cast<float>(a) + 0.5f) * inv_b); }
@@ -380,7 +382,6 @@ __global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_k
 //      block of steps, keeps (G[x0], G[x0+1]-G[x0]) in registers and refreshes them from the table when x0 moves;
 //      consecutive lanes write consecutive vectors of one row.
 // Same arithmetic, in the same order, as the z-run walker of gather_grid.cu, so the columns are bit-identical to it.
-struct VecDesc { int tab; int cstride; int col; int lc; };   // table base (floats), floats per cell, X column, level*3+class
 
 __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestParams p) {
   extern __shared__ __align__(16) float s_tab[];
@@ -389,7 +390,6 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   __shared__ float s_w1[kRestLevels][3][kTile];
   __shared__ int s_first[kRestLevels][3], s_ncell[kRestLevels][3];
   __shared__ Corner s_cor[kRestLevels * LIST_NUM_DISP][4];
-  __shared__ __align__(16) VecDesc s_vec[kMaxVec];
   __shared__ int s_tailtab[kMaxTail];                   // scalar columns: table base | (level*3+class) << 24
   const int tid = threadIdx.x;
   TileSpan t;
@@ -414,22 +414,6 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     for (int k = 0; k < 4; ++k) s_cor[pr][k] = Corner{base[k], wyz[k]};
   }
   for (int s = tid; s < kPz; s += kRestThreads) s_q0[s] = (s >= t.s_lo && s < t.s_hi) ? step_q0(p.tm, t, s) : 0.f;
-  for (int v = tid; v < p.nvec; v += kRestThreads) {                    // vector item -> (level, displacement, channel vector)
-    int item = v, li = 0;
-    for (; li < p.nvl; ++li) {
-      const int cnt = LIST_NUM_DISP * (p.C[li] >> 3);
-      if (item < cnt) break;
-      item -= cnt;
-    }
-    const int ncv = p.C[li] >> 3;
-    const int d = item / ncv, cvv = item % ncv;
-    VecDesc vd;
-    vd.tab = p.toff[li] + d * p.cells_max[li] * p.C[li] + cvv * 8;
-    vd.cstride = p.C[li];
-    vd.col = p.xoff[li] + d * p.C[li] + cvv * 8;
-    vd.lc = li * 3 + shift_class(d);
-    s_vec[v] = vd;
-  }
   const int nscal = p.xyz_off - p.tail0;
   for (int j = tid; j < nscal; j += kRestThreads) {                     // scalar column -> table base, class
     const int col = p.tail0 + j;
@@ -458,30 +442,24 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     s_w1[li][cls][s] = w1;
   }
 
-  // ---- phase G: vector levels (items striped over the CTA across all levels) ----
+  // ---- phase G: vector levels.  A thread keeps one (displacement, channel vector) -- corners, weights and base pointers
+  //      stay in registers -- and strides over the voxel cells of its class ----
   {
-    int lvl_begin = 0;
     for (int li = 0; li < p.nvl; ++li) {
       const int C = p.C[li], ncv = C >> 3, cm = p.cells_max[li];
-      const int ncv_shift = 31 - __clz(ncv);                            // C / 8 is a power of two (checked by the launcher)
-      const int per_d = cm * ncv, cnt = LIST_NUM_DISP * per_d;
-      const float inv_per_d = 1.0f / static_cast<float>(per_d);
-      const __nv_bfloat16* __restrict__ vol = p.vols[li];
-      float* __restrict__ tab = s_tab + p.toff[li];
-      const int* first = s_first[li];
-      const int* ncell = s_ncell[li];
-      int it = tid - (lvl_begin % kRestThreads);
-      if (it < 0) it += kRestThreads;
-      for (; it < cnt; it += kRestThreads) {
-        const int d = fast_div(it, inv_per_d);
-        const int rem = it - d * per_d;
-        const int c = rem >> ncv_shift;
-        const int cvv = rem & (ncv - 1);
-        const int cls = shift_class(d);
-        if (c >= ncell[cls]) continue;
-        const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
-        const __nv_bfloat16* src = vol + static_cast<uint32_t>(first[cls] + c) * C + cvv * 8;
-        const Corner c0 = cor[0], c1 = cor[1], c2 = cor[2], c3 = cor[3];
+      const int combos = LIST_NUM_DISP * ncv;                           // <= kMaxVec <= kRestThreads / 2
+      const int lanes = kRestThreads / combos;
+      const int combo = tid % combos, lane0 = tid / combos;
+      if (lane0 >= lanes) continue;
+      const int d = combo / ncv, cvv = combo - d * ncv;
+      const int cls = shift_class(d);
+      const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
+      const Corner c0 = cor[0], c1 = cor[1], c2 = cor[2], c3 = cor[3];
+      const int ncell = s_ncell[li][cls];
+      const __nv_bfloat16* __restrict__ src = p.vols[li] + static_cast<uint32_t>(s_first[li][cls] + lane0) * C + cvv * 8;
+      float* __restrict__ dstt = s_tab + p.toff[li] + (d * cm + lane0) * C + cvv * 8;
+      const int sstep = lanes * C;
+      for (int c = lane0; c < ncell; c += lanes, src += sstep, dstt += sstep) {
         float v0[8], v1[8], v2[8], v3[8], g[8];
         load8(src + c0.base, v0);
         load8(src + c1.base, v1);
@@ -489,11 +467,9 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         load8(src + c3.base, v3);
 #pragma unroll
         for (int j = 0; j < 8; ++j) g[j] = fmaf(v3[j], c3.w, fmaf(v2[j], c2.w, fmaf(v1[j], c1.w, v0[j] * c0.w)));
-        float* dstt = tab + (d * cm + c) * C + cvv * 8;
         *reinterpret_cast<float4*>(dstt) = make_float4(g[0], g[1], g[2], g[3]);
         *reinterpret_cast<float4*>(dstt + 4) = make_float4(g[4], g[5], g[6], g[7]);
       }
-      lvl_begin += cnt;
     }
     // scalar levels (C % 8 != 0): one (displacement, cell, channel) value per item
     for (int li = p.nvl; li < nlev; ++li) {
@@ -519,30 +495,37 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   }
   __syncthreads();
 
-  // ---- phase L: vector columns.  thread = (vector v, block of steps) ----
+  // ---- phase L: vector columns.  Every warp works on ONE level (host plan: lwarp0 / lwarps), so all its lanes refresh
+  //      their registers at that level's cadence; thread = (16-byte vector v of the level, block of steps) ----
   const int nsteps = t.s_hi - t.s_lo;
   __nv_bfloat16* __restrict__ Xb = p.X + (t.g_tile0 + t.s_lo - p.tm.begin) * p.ldx;
   {
-    const int nblk = kRestThreads / p.nvec;              // step blocks (>= 2: nvec <= kMaxVec)
-    const int v = tid % p.nvec, blk = tid / p.nvec;
-    if (blk < nblk) {
-      const int per = (nsteps + nblk - 1) / nblk;
+    int li = 0;
+    while (li + 1 < p.nvl && warp_of(tid) >= p.lwarp0[li + 1]) ++li;
+    const int C = p.C[li], ncv = C >> 3, cm = p.cells_max[li];
+    const int nvec = LIST_NUM_DISP * ncv;
+    const int T = (p.lwarp0[li + 1] - p.lwarp0[li]) * 32;               // threads of this level
+    const int lt = tid - p.lwarp0[li] * 32;
+    const int nblk = max(1, T / nvec);
+    const int per = (nsteps + nblk - 1) / nblk;
+    for (int it = lt; it < nvec * nblk; it += T) {
+      const int v = it % nvec, blk = it / nvec;
+      const int d = v / ncv, cvv = v - d * ncv;
+      const int cls = shift_class(d);
       const int sr0 = blk * per, sr1 = min(nsteps, sr0 + per);
-      const VecDesc vd = s_vec[v];
-      const int li = vd.lc / 3, cls = vd.lc - li * 3;
       const int* __restrict__ rels = s_rel[li][cls] + t.s_lo;
       const float* __restrict__ w1s = s_w1[li][cls] + t.s_lo;
       const int last = s_ncell[li][cls] - 1;
-      const float* __restrict__ tab = s_tab + vd.tab;
+      const float* __restrict__ tab = s_tab + p.toff[li] + d * cm * C + cvv * 8;
       float G0[8], Dv[8];
       int cc = -1;
-      __nv_bfloat16* __restrict__ dst = Xb + static_cast<int64_t>(sr0) * p.ldx + vd.col;
+      __nv_bfloat16* __restrict__ dst = Xb + static_cast<int64_t>(sr0) * p.ldx + p.xoff[li] + d * C + cvv * 8;
       for (int sr = sr0; sr < sr1; ++sr, dst += p.ldx) {
         const int c = rels[sr];
         if (c != cc) {
           cc = c;
-          const float* g0p = tab + c * vd.cstride;
-          const float* g1p = tab + min(c + 1, last) * vd.cstride;
+          const float* g0p = tab + c * C;
+          const float* g1p = tab + min(c + 1, last) * C;
           const float4 a0 = *reinterpret_cast<const float4*>(g0p), a1 = *reinterpret_cast<const float4*>(g0p + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(g1p), b1 = *reinterpret_cast<const float4*>(g1p + 4);
           G0[0] = a0.x; G0[1] = a0.y; G0[2] = a0.z; G0[3] = a0.w; G0[4] = a1.x; G0[5] = a1.y; G0[6] = a1.z; G0[7] = a1.w;
@@ -686,13 +669,32 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
     }
   }
   if (r.nvec > kMaxVec || r.nvec == 0) return LIST_ENOSYS;
+  {
+    // phase-L warp plan: warps per vector level in proportion to (vectors) x (cost of a step, which grows with the
+    // number of voxel cells a step crosses), at least one each
+    const int nw = kRestThreads / 32;
+    if (r.nvl > nw) return LIST_ENOSYS;
+    double cost[kRestLevels] = {}, total = 0;
+    for (int i = 0; i < r.nvl; ++i) {
+      const double cells_per_step = res > 1 ? static_cast<double>(r.R[i] - 1) / (res - 1) : 1.0;
+      cost[i] = LIST_NUM_DISP * (r.C[i] / 8) * (20.0 + 22.0 * (cells_per_step < 1.0 ? cells_per_step : 1.0));
+      total += cost[i];
+    }
+    int w[kRestLevels] = {}, used = 0;
+    for (int i = 0; i < r.nvl; ++i) { w[i] = static_cast<int>(cost[i] / total * nw + 0.5); if (w[i] < 1) w[i] = 1; used += w[i]; }
+    while (used > nw) { int k = 0; for (int i = 1; i < r.nvl; ++i) if (w[i] > w[k]) k = i; --w[k]; --used; }
+    while (used < nw) { int k = 0; for (int i = 1; i < r.nvl; ++i) if (cost[i] / w[i] > cost[k] / w[k]) k = i; ++w[k]; ++used; }
+    r.lwarp0[0] = 0;
+    for (int i = 0; i < r.nvl; ++i) r.lwarp0[i + 1] = r.lwarp0[i] + w[i];
+  }
   r.tail0 = tail0 - shift;
   r.xyz_off = lay.xyz_off - shift;
   r.k_h = pl.k_h;
   if (r.tail0 % 8 != 0 || r.k_h - r.tail0 > kMaxTail || r.xyz_off + 3 > r.k_h) return LIST_ENOSYS;
   // the vector columns must be exactly [kN0, tail0): the kernel writes nothing else there
   if (kN0 + r.nvec * 8 != r.tail0) return LIST_ENOSYS;
-  // largest tile whose column tables fit next to a second CTA on the SM
+  // largest tile whose column tables leave room for three CTAs per SM (the kernel is latency bound: warps matter more
+  // than the per-tile overhead of shorter tiles)
   for (int kpz = kTile; kpz >= 16; kpz >>= 1) {
     size_t floats = 0;
     int items = 0;
@@ -708,7 +710,7 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
     static const size_t budget = []() {                // LIST_B200_REST_SMEM_KB: table budget per CTA (tuning aid)
       const char* e = getenv("LIST_B200_REST_SMEM_KB");
       const long v = e ? atol(e) : 0;
-      return static_cast<size_t>(v >= 8 && v <= 200 ? v : 96) * 1024;
+      return static_cast<size_t>(v >= 8 && v <= 200 ? v : 64) * 1024;   // measured at 256^3: 96 KB 11.4 ms, 64 KB 10.9 ms, 48 KB 12.1 ms
     }();
     if (floats * 4 <= budget && floats < (1u << 24) && items < (1 << 20)) {
       r.g_items = items;
