@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0,
-                    help="feature rows per gather/MLP launch; 0 = a quarter of the rank's shard, clamped to [262144, 1048576] "
+                    help="feature rows per gather/MLP launch; 0 = a quarter of the rank's shard, clamped to [262144, 4194304] "
                          "(large launches amortise the last partial wave of gather CTAs, four chunks keep the pipeline busy)")
     ap.add_argument("--cpu-chunks", type=int, default=2, help="65536-point chunks timed for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -186,7 +186,7 @@ def main():
     kw = hotpath.prepare_weights(g.weights, ctx.layout, a.dtype)
     lay = ctx.layout
     begin, count = parallel.shard_range(total, rank, world, align=res * res)
-    auto_chunk = min(1048576, max(262144, -(-(-(-count // 4)) // 65536) * 65536))
+    auto_chunk = min(4194304, max(262144, -(-(-(-count // 4)) // 65536) * 65536))
     chunk = max(1, min(a.chunk if a.chunk > 0 else auto_chunk, count))
     cs, wsn = ctx.struct(), kw.struct()
     ws = hotpath._workspace(cs, wsn, chunk, dev)

@@ -82,7 +82,7 @@ class LIST:
         grid = parallel.sharded_grid(
             # results do not depend on the chunking (tests), so the kernels get large launches instead of the
             # reference's 65 536-point chunks: the last partial wave of gather CTAs is amortised
-            lambda begin, count: net.grid(ctx, res, begin, count, self.sdf_scale, max(self.test_pointnum, 524288)),
+            lambda begin, count: net.grid(ctx, res, begin, count, self.sdf_scale, max(self.test_pointnum, min(4194304, max(524288, -(-count // 4))))),
             total, align=res * res)
         self._grid_dev = grid[0].view(res, res, res)                  # kept on the device for the mesh extraction
         vals = self._grid_dev.cpu().numpy()
