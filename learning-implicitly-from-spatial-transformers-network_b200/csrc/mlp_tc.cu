@@ -129,7 +129,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     }
     for (int a = 0; a < NA; ++a) mbar_init(afull_bar(a), 1);
     mbar_init(dfull_bar, 1);
-    mbar_init(hready_bar, 128 * CG);
+    mbar_init(hready_bar, 4 * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<CG>(tmem_slot);
@@ -275,6 +275,15 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
     const uint32_t hready_remote = (CG == 2) ? mapa(hready_bar, 0) : hready_bar;
     const float bias3 = __ldg(b3);
     const int r_in_tile = quarter * 32 + lane;                         // row of the CTA's 128-row tile
+    // one arrival per WARP (every lane has executed tcgen05.fence::before_thread_sync; __syncwarp orders them before
+    // lane 0's release-arrive): 4*CG arrivals complete a phase instead of 128*CG, half of them remote
+    auto arrive_hready = [&]() {
+      __syncwarp();
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(hready_remote);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      }
+    };
     uint32_t dphase = 0;
     int etno = 0;
     const bool estamp = warp == kEpiWarp0 && lane == 0;
@@ -304,8 +313,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
           }
         }
         tc_fence_before();
-        if (CG == 2) mbar_arrive_cluster(hready_remote);
-        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+        arrive_hready();
         continue;
       }
       if (add) {
@@ -372,8 +380,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tmem_wait_st();
       tc_fence_before();
       if (estamp) stamp(etno, 7);
-      if (CG == 2) mbar_arrive_cluster(hready_remote);
-      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      arrive_hready();
       // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
@@ -398,8 +405,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tmem_wait_st();
       tc_fence_before();
       if (estamp) stamp(etno, 9);
-      if (CG == 2) mbar_arrive_cluster(hready_remote);
-      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      arrive_hready();
       // ---- after fc_2: sdf = (relu(acc + b2) · w3 + b3) / out_div ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
@@ -420,8 +426,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       }
       tc_fence_before();
       if (estamp) stamp(etno, 11);
-      if (CG == 2) mbar_arrive_cluster(hready_remote);
-      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(hready_bar) : "memory");
+      arrive_hready();
       if (row < rows) sdf[row] = __fdiv_rn(acc + bias3, out_div);
     }
   }
