@@ -8,6 +8,9 @@
 //   A_KMAJOR : A(m,k) = A[m*lda + k]   else A(m,k) = A[k*lda + m]
 //   B_KMAJOR : B(k,n) = B[n*ldb + k]   else B(k,n) = B[k*ldb + n]
 // 128x128x16 tiles, 256 threads, 8x8 outputs per thread, register-prefetched double buffering.
+// Split-K (gridDim.z > 1): every z-slice reduces its own K range and adds it to C with fp32 atomics -- used for the
+// weight gradients (M x N = 512 x 3648 outputs over K = 16 384 rows would otherwise run on 116 CTAs); only valid for
+// plain accumulation (accumulate = 1, no bias / ReLU / mask), which is what the launcher enforces.
 #pragma once
 #include "common.cuh"
 
@@ -125,13 +128,18 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
-  const int nk = (K + 15) / 16;
-  load_tile(0);
+  // K range of this z-slice (whole tiles of 16)
+  const int nk_all = (K + 15) / 16;
+  const int nk_per = (nk_all + gridDim.z - 1) / gridDim.z;
+  const int kt0 = blockIdx.z * nk_per;
+  const int nk = min(nk_all - kt0, nk_per);
+  if (nk <= 0) return;
+  load_tile(kt0 * 16);
   store_tile(0);
   __syncthreads();
   for (int kt = 0; kt < nk; ++kt) {
     const int buf = kt & 1;
-    if (kt + 1 < nk) load_tile((kt + 1) * 16);
+    if (kt + 1 < nk) load_tile((kt0 + kt + 1) * 16);
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
@@ -171,7 +179,9 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
         v[j] = x;
       }
       float* dst = C + static_cast<int64_t>(m) * ldc + n;
-      if (n + 3 < N) {
+      if (gridDim.z > 1) {
+        for (int j = 0; j < 4 && n + j < N; ++j) atomicAdd(dst + j, v[j]);
+      } else if (n + 3 < N) {
         float4 o = make_float4(v[0], v[1], v[2], v[3]);
         if (ep.accumulate) {
           const float4 c = *reinterpret_cast<const float4*>(dst);
@@ -190,6 +200,14 @@ inline int sgemm(const float* A, int64_t lda, const float* B, int64_t ldb, float
                  int N, int K, const GemmEpilogue& ep, cudaStream_t st) {
   if (M <= 0 || N <= 0) return LIST_OK;
   dim3 grid((M + 127) / 128, (N + 127) / 128);
+  // split K when the output alone cannot fill the GPU and the epilogue is a plain accumulation
+  if (ep.accumulate && !ep.bias && !ep.relu && !ep.mask && K >= 2048) {
+    const int tiles = grid.x * grid.y;
+    int split = (2 * 148 + tiles - 1) / tiles;                    // aim at ~2 CTAs per SM
+    const int max_split = K / 1024;
+    if (split > max_split) split = max_split;
+    if (split > 1) grid.z = split;
+  }
   sgemm_kernel<A_KMAJOR, B_KMAJOR><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, M, N, K, ep);
   LIST_LAUNCH_CHECK("sgemm_kernel");
   return LIST_OK;
