@@ -103,6 +103,7 @@ struct RestParams {
   int R[kRestLevels], C[kRestLevels], xoff[kRestLevels];   // xoff: first column of the level in the hoisted row
   int cells_max[kRestLevels];       // table rows per (level, displacement)
   int toff[kRestLevels];            // first float of the level's tables in shared memory
+  int tab_floats;                   // floats of all column tables (the per-step tables follow)
   int nvl, nsl;                     // vector levels [0, nvl), scalar levels [nvl, nvl + nsl)
   int lwarp0[kRestLevels + 1];      // phase L: warps [lwarp0[i], lwarp0[i+1]) work on vector level i
   int nvec;                         // 16-byte items per row of the vector levels
@@ -386,8 +387,10 @@ __global__ void __launch_bounds__(kN0 / V, LIST_ADDEND_MINBLOCKS) hoist_addend_k
 __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestParams p) {
   extern __shared__ __align__(16) float s_tab[];
   __shared__ float s_q0[kTile];
-  __shared__ int s_rel[kRestLevels][3][kTile];          // voxel index relative to the class's first one
-  __shared__ float s_w1[kRestLevels][3][kTile];
+  // per (level, class, step), sized by the tile length and placed behind the column tables in dynamic shared memory:
+  // voxel index relative to the class's first one (fits a byte: cells_max <= 255) and the weight of its right neighbour
+  float* const s_w1 = s_tab + p.tab_floats;                                         // [nlev*3][kPz]
+  unsigned char* const s_rel = reinterpret_cast<unsigned char*>(s_w1 + kRestLevels * 3 * p.tm.kPz);   // [nlev*3][kPz]
   __shared__ int s_first[kRestLevels][3], s_ncell[kRestLevels][3];
   __shared__ Corner s_cor[kRestLevels * LIST_NUM_DISP][4];
   __shared__ int s_tailtab[kMaxTail];                   // scalar columns: table base | (level*3+class) << 24
@@ -438,8 +441,8 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       rel = min(ax.i0 - s_first[li][cls], p.cells_max[li] - 1);
       w1 = ax.w1;
     }
-    s_rel[li][cls][s] = rel;
-    s_w1[li][cls][s] = w1;
+    s_rel[lc * kPz + s] = static_cast<unsigned char>(rel);
+    s_w1[lc * kPz + s] = w1;
   }
 
   // ---- phase G: vector levels.  A thread keeps one (displacement, channel vector) -- corners, weights and base pointers
@@ -513,8 +516,8 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       const int d = v / ncv, cvv = v - d * ncv;
       const int cls = shift_class(d);
       const int sr0 = blk * per, sr1 = min(nsteps, sr0 + per);
-      const int* __restrict__ rels = s_rel[li][cls] + t.s_lo;
-      const float* __restrict__ w1s = s_w1[li][cls] + t.s_lo;
+      const unsigned char* __restrict__ rels = s_rel + (li * 3 + cls) * kPz + t.s_lo;
+      const float* __restrict__ w1s = s_w1 + (li * 3 + cls) * kPz + t.s_lo;
       const int last = s_ncell[li][cls] - 1;
       const float* __restrict__ tab = s_tab + p.toff[li] + d * cm * C + cvv * 8;
       float G0[8], Dv[8];
@@ -569,10 +572,10 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
           const int tt = s_tailtab[col];
           const int lc = tt >> 24, tab = tt & 0xffffff;
           const int li = lc / 3, cls = lc - li * 3;
-          const int c = s_rel[li][cls][s];
+          const int c = s_rel[lc * kPz + s];
           const int c1 = min(c + 1, s_ncell[li][cls] - 1);
           const float g0 = s_tab[tab + c * p.C[li]], g1 = s_tab[tab + c1 * p.C[li]];
-          val = fmaf(g1 - g0, s_w1[li][cls][s], g0);
+          val = fmaf(g1 - g0, s_w1[lc * kPz + s], g0);
         } else if (col < nscal + 3) {
           const int a = col - nscal;
           val = a == 0 ? s_q0[s] : (a == 1 ? t.qy : t.qz);
@@ -712,10 +715,13 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       const long v = e ? atol(e) : 0;
       return static_cast<size_t>(v >= 8 && v <= 200 ? v : 64) * 1024;   // measured at 256^3: 96 KB 11.4 ms, 64 KB 10.9 ms, 48 KB 12.1 ms
     }();
-    if (floats * 4 <= budget && floats < (1u << 24) && items < (1 << 20)) {
+    bool fits_byte = true;
+    for (int i = 0; i < nl; ++i) fits_byte = fits_byte && r.cells_max[i] <= 255;
+    if (floats * 4 <= budget && floats < (1u << 24) && items < (1 << 20) && fits_byte) {
       r.g_items = items;
       r.tm.kPz = kpz;
-      *smem = floats * 4;
+      r.tab_floats = static_cast<int>((floats + 3) / 4 * 4);
+      *smem = static_cast<size_t>(r.tab_floats) * 4 + static_cast<size_t>(kRestLevels) * 3 * kpz * (4 + 1);
       return LIST_OK;
     }
   }
