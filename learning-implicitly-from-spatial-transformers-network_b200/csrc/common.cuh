@@ -37,6 +37,37 @@ __host__ __device__ __forceinline__ int64_t min64(int64_t a, int64_t b) { return
 
 constexpr float kDisplacement = 0.0722f;   // reference network/modules.py:205
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FADD2) ----
+// Two IEEE round-to-nearest operations per instruction, each lane bit-identical to the scalar fmaf / +.  Measured on
+// B200 (scripts/microbench/ffma2.cu): FFMA issues one warp instruction per cycle and scheduler (127 FMA/clk/SM), FFMA2
+// one per 2.17 cycles (118 FMA/clk/SM) -- the packed form saves issue slots, not pipe time.  It pays in the MLP
+// epilogues (one warp per scheduler, issue bound); in the gather kernels it was neutral to slower
+// (profiles/r01_exp_packed_fp32_and_addend_variants.txt).  ptxas folds a {s, s} operand into the scalar-broadcast form.
+__device__ __forceinline__ unsigned long long f2_pack(float2 a) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+  return r;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long r) {
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+  return d;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {        // a * b + c
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)), "l"(f2_pack(c)));
+  return f2_unpack(d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(f2_pack(a)), "l"(f2_pack(b)));
+  return f2_unpack(d);
+}
+// two bf16 (one 32-bit word, low half first) -> fp32 pair
+__device__ __forceinline__ float2 bf16x2_to_f2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+
 // ---- 8-wide channel vectors (16 B of bf16 / 32 B of fp32) ----
 __device__ __forceinline__ void load8(const float* __restrict__ p, float v[8]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -60,6 +91,12 @@ __device__ __forceinline__ void store8(float* __restrict__ p, const float v[8]) 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);   // .x = lo (low 16 bits)
   return *reinterpret_cast<const uint32_t*>(&h);
+}
+// max(x, 0) folded into the conversion (F2FP.RELU): negative -> +0, NaN stays NaN like torch's relu
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
 }
 __device__ __forceinline__ void store8(__nv_bfloat16* __restrict__ p, const float v[8]) {
   uint4 u;

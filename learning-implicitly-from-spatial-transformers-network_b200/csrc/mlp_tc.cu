@@ -341,18 +341,19 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
             for (int i = 0; i < 4; ++i) {
               const uint32_t w4[4] = {pq[i].x, pq[i].y, pq[i].z, pq[i].w};
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                v[8 * i + 2 * e] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e]) + __uint_as_float(w4[e] << 16), 0.f));
-                v[8 * i + 2 * e + 1] = __float_as_uint(fmaxf(__uint_as_float(v[8 * i + 2 * e + 1]) + __uint_as_float(w4[e] & 0xffff0000u), 0.f));
+              for (int e = 0; e < 4; ++e) {                  // packed add, relu folded into the bf16 conversion
+                const float2 sum = fadd2(make_float2(__uint_as_float(v[8 * i + 2 * e]), __uint_as_float(v[8 * i + 2 * e + 1])),
+                                         bf16x2_to_f2(w4[e]));
+                v[8 * i + 2 * e] = __float_as_uint(sum.x);
+                v[8 * i + 2 * e + 1] = __float_as_uint(sum.y);
+                u[4 * i + e] = pack_bf16x2_relu(sum.x, sum.y);
               }
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) u[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
             tmem_st16(tq + j * 16, u);
             if (dbg1 != nullptr && row < rows) {
               float* const drow = dbg1 + row * N0 + j * 32;
 #pragma unroll
-              for (int i = 0; i < 32; ++i) drow[i] = __uint_as_float(v[i]);
+              for (int i = 0; i < 32; ++i) drow[i] = fmaxf(__uint_as_float(v[i]), 0.f);
             }
           }
           named_bar_sync(1, 128);                            // all four epilogue warps are done with the box ...
@@ -366,8 +367,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 bb = *reinterpret_cast<const float2*>(s_b0 + j * 32 + 2 * i);
-          u[i] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f),
-                             fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
+          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+          u[i] = pack_bf16x2_relu(sum.x, sum.y);
         }
         tmem_st16(tq + j * 16, u);
         if (dbg1 != nullptr && row < rows) {               // diagnostic copy of relu(fc_0) (fp32, pre-rounding)
@@ -392,8 +393,8 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 bb = *reinterpret_cast<const float2*>(s_b1 + j * 32 + 2 * i);
-          u[i] = pack_bf16x2(fmaxf(__uint_as_float(v[2 * i]) + bb.x, 0.f),
-                             fmaxf(__uint_as_float(v[2 * i + 1]) + bb.y, 0.f));
+          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+          u[i] = pack_bf16x2_relu(sum.x, sum.y);
         }
         tmem_st16(tq + j * 16, u);
         if (dbg2 != nullptr && row < rows) {
@@ -410,14 +411,18 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(etno, 10);
-      float acc = 0.f;
+      float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll 1
       for (int j = 0; j < N2 / 32; ++j) {
         uint32_t v[32];
         tmem_ld32(tq + 256 + j * 32, v);
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          acc = fmaf(fmaxf(__uint_as_float(v[i]) + s_b2[j * 32 + i], 0.f), s_w3[j * 32 + i], acc);
+        for (int i = 0; i < 16; ++i) {                       // even / odd columns accumulate in the two packed lanes
+          const float2 bb = *reinterpret_cast<const float2*>(s_b2 + j * 32 + 2 * i);
+          const float2 ww = *reinterpret_cast<const float2*>(s_w3 + j * 32 + 2 * i);
+          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+          acc2 = ffma2(make_float2(fmaxf(sum.x, 0.f), fmaxf(sum.y, 0.f)), ww, acc2);
+        }
         if (dbg3 != nullptr && row < rows) {
 #pragma unroll
           for (int i = 0; i < 32; ++i)
@@ -427,7 +432,7 @@ mlp_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ C
       tc_fence_before();
       if (estamp) stamp(etno, 11);
       arrive_hready();
-      if (row < rows) sdf[row] = __fdiv_rn(acc + bias3, out_div);
+      if (row < rows) sdf[row] = __fdiv_rn((acc2.x + acc2.y) + bias3, out_div);
     }
   }
 
