@@ -379,7 +379,9 @@ def main():
         e2e = {"value": total * e_steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
                "d2h_bytes_per_step": runner.d2h_bytes, "steps": e_steps,
                "what": "parallel.ShardedHostRunner: pinned host per-image tensors (fp32, reference layout) -> H2D "
-                       + ("(1/N of every tensor per rank + one NCCL all_gather over NVLink) " if world > 1 else "")
+                       + ("(1/N of every tensor per rank + one NCCL all_gather over NVLink) " if world > 1 else
+                          "(C ABI list_sdf_grid_host: big volumes upload behind the projection and the first addend "
+                          "gather, every chunk downloads behind the next chunk's kernels) ")
                        + "-> prep kernels -> projection + gather + MLP over the rank's grid shard -> D2H of its SDF values "
                        "into pinned host memory; wall clock, max over ranks"}
         # sanity: same numbers as the resident path

@@ -122,6 +122,10 @@ struct Pipe {
   int device = -1;
   cudaStream_t lo = nullptr, hi = nullptr;
   cudaEvent_t fork = nullptr, ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  // host-buffer entry point (list_sdf_grid_host): copy stream, "coarse tensors uploaded", "all tensors uploaded",
+  // "these SDF values are final", "last download enqueued"
+  cudaStream_t cp = nullptr;
+  cudaEvent_t cfork = nullptr, small = nullptr, big = nullptr, item = nullptr, cdone = nullptr;
 };
 static constexpr int kMaxPipeDevices = 16;
 static thread_local Pipe g_pipes[kMaxPipeDevices];
@@ -136,7 +140,9 @@ static int get_pipe(Pipe** out) {
     LIST_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
     LIST_CUDA(cudaStreamCreateWithPriority(&p.lo, cudaStreamNonBlocking, least));
     LIST_CUDA(cudaStreamCreateWithPriority(&p.hi, cudaStreamNonBlocking, greatest));
+    LIST_CUDA(cudaStreamCreateWithFlags(&p.cp, cudaStreamNonBlocking));
     LIST_CUDA(cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming));
+    for (cudaEvent_t* e : {&p.cfork, &p.small, &p.big, &p.item, &p.cdone}) LIST_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     for (int i = 0; i < 2; ++i) {
       LIST_CUDA(cudaEventCreateWithFlags(&p.ready[i], cudaEventDisableTiming));
       LIST_CUDA(cudaEventCreateWithFlags(&p.freed[i], cudaEventDisableTiming));
@@ -157,6 +163,34 @@ static bool hoist_enabled() {
 static bool overlap_enabled() {
   const char* e = getenv("LIST_B200_OVERLAP");
   return !(e && e[0] == '0');
+}
+
+// Hooks of the host-buffer entry point into the dense-grid evaluation.  Upload, evaluation and download overlap:
+//   * the coarse per-image tensors (maps, levels with R <= 16, T) are uploaded and prepared first; the projection and
+//     the addend part of the first chunk's gather only need those, so they run while the big volumes are still on the
+//     wire.  `late` (wait for the upload, prepare the remaining levels) runs on the gather stream right before the
+//     first kernel that reads them;
+//   * every chunk's SDF values go to the host on the copy stream as soon as their MLP launch is done.
+struct GridHooks {
+  cudaEvent_t uploaded = nullptr;                   // recorded on the copy stream after the last H2D copy
+  int (*late)(void* user, cudaStream_t s) = nullptr;
+  void* user = nullptr;
+  float* sdf_host = nullptr;                        // [B, count] like the device-side sdf; NULL: no download
+  cudaStream_t copy = nullptr;
+  cudaEvent_t item = nullptr;
+};
+static int hook_late(const GridHooks* h, cudaStream_t s) {
+  if (!h || !h->late) return LIST_OK;
+  LIST_CUDA(cudaStreamWaitEvent(s, h->uploaded, 0));
+  return h->late(h->user, s);
+}
+// values [off, off + n) of the SDF buffer are final once the work enqueued on `s` so far is done
+static int hook_download(const GridHooks* h, const float* sdf_dev, int64_t off, int64_t n, cudaStream_t s) {
+  if (!h || !h->sdf_host || n <= 0) return LIST_OK;
+  LIST_CUDA(cudaEventRecord(h->item, s));
+  LIST_CUDA(cudaStreamWaitEvent(h->copy, h->item, 0));
+  LIST_CUDA(cudaMemcpyAsync(h->sdf_host + off, sdf_dev + off, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToHost, h->copy));
+  return LIST_OK;
 }
 
 // Runs `n_items` (gather_i -> mlp_i) pairs.  gather(i, X, stream) fills X; mlp(i, X, stream) consumes it.
@@ -499,9 +533,9 @@ int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32
       });
 }
 
-int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
-                  int64_t count, float* sdf, float sdf_scale, int64_t chunk_rows, void* workspace, size_t workspace_bytes,
-                  void* stream) {
+static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
+                     int64_t count, float* sdf, float sdf_scale, int64_t chunk_rows, void* workspace, size_t workspace_bytes,
+                     void* stream, const GridHooks* hooks) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   ListLayout lay;
@@ -520,11 +554,15 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
   const char* nf = getenv("LIST_B200_NO_FUSED");
   bool fused = ctx->dtype == LIST_BF16 && !(nf && nf[0] == '1') && fused_default();
   int b0 = 0;
+  bool late_done = false;
   if (fused) {
+    if ((rc = hook_late(hooks, st))) return rc;
+    late_done = true;
     for (; b0 < ctx->B; ++b0) {
       rc = sdf_grid_fused(ctx, w, b0, res, bb_min, bb_max, begin, count, sdf + static_cast<int64_t>(b0) * count, sdf_scale, st);
       if (rc == LIST_ENOSYS && b0 == 0) { fused = false; break; }
       if (rc) return rc;
+      if ((rc = hook_download(hooks, sdf, static_cast<int64_t>(b0) * count, count, st))) return rc;
     }
     if (fused) return LIST_OK;
   }
@@ -553,18 +591,27 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
     if ((rc = hoist::prepare(ctx, w, pl, hbuf, st))) return rc;
     return run_chunks(
         per_image * ctx->B, xbuf, overlap_enabled(), st,
-        [&](int64_t i, void* X, cudaStream_t s) {
+        [&](int64_t i, void* X, cudaStream_t s) -> int {
           int b; int64_t n0, n;
           span(i, b, n0, n);
+          if (i == 0 && !late_done && hooks && hooks->late) {
+            // the addend only reads the projected tensors; everything uploaded late is first read by the other part
+            int r2 = hoist::gather(ctx, w, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, hoist::kPartAddend, s);
+            if (r2) return r2;
+            if ((r2 = hook_late(hooks, s))) return r2;
+            return hoist::gather(ctx, w, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, hoist::kPartRest, s);
+          }
           return hoist::gather(ctx, w, pl, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, pl.k_h, 3, s);
         },
-        [&](int64_t i, void* X, cudaStream_t s) {
+        [&](int64_t i, void* X, cudaStream_t s) -> int {
           int b; int64_t n0, n;
           span(i, b, n0, n);
-          return mlp_tc_fwd_hoisted(w, pl.hoist_cols, pl.k_h - 512, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0,
-                                    sdf_scale, mlp_variant(), nullptr, nullptr, nullptr, nullptr, s);
+          const int r2 = mlp_tc_fwd_hoisted(w, pl.hoist_cols, pl.k_h - 512, X, pl.k_h, n, sdf + static_cast<int64_t>(b) * count + n0,
+                                            sdf_scale, mlp_variant(), nullptr, nullptr, nullptr, nullptr, s);
+          return r2 ? r2 : hook_download(hooks, sdf, static_cast<int64_t>(b) * count + n0, n, s);
         });
   }
+  if (!late_done && (rc = hook_late(hooks, st))) return rc;
   return run_chunks(
       per_image * ctx->B, xbuf, two && overlap_enabled(), st,
       [&](int64_t i, void* X, cudaStream_t s) {
@@ -572,12 +619,20 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
         span(i, b, n0, n);
         return grid_gather(ctx, b, res, bb_min, bb_max, begin + n0, n, X, lay.k_pad, s);
       },
-      [&](int64_t i, void* X, cudaStream_t s) {
+      [&](int64_t i, void* X, cudaStream_t s) -> int {
         int b; int64_t n0, n;
         span(i, b, n0, n);
-        return list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, mlp_ws,
-                            workspace_bytes - mlp_off, s);
+        const int r2 = list_mlp_fwd(w, X, lay.k_pad, n, sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, mlp_ws,
+                                    workspace_bytes - mlp_off, s);
+        return r2 ? r2 : hook_download(hooks, sdf, static_cast<int64_t>(b) * count + n0, n, s);
       });
+}
+
+int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
+                  int64_t count, float* sdf, float sdf_scale, int64_t chunk_rows, void* workspace, size_t workspace_bytes,
+                  void* stream) {
+  return grid_impl(ctx, w, res, bb_min, bb_max, begin, count, sdf, sdf_scale, chunk_rows, workspace, workspace_bytes, stream,
+                   nullptr);
 }
 
 // ---- host-buffer variant -----------------------------------------------------------------
@@ -644,20 +699,41 @@ int list_sdf_grid_host(const float* const* maps_host, const int32_t* map_ch, con
   LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(dev_scratch) & 255) == 0, "list_sdf_grid_host: dev_scratch must be 256B aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(dev_scratch);
+  Pipe* pp = nullptr;
+  int rc;
+  if ((rc = get_pipe(&pp))) return rc;
+  // Uploads run on the copy stream, ordered after the caller's stream: T, maps and the coarse levels (R <= 16: all the
+  // projection and the addend gather read) first, then the other levels from coarse to fine.
+  LIST_CUDA(cudaEventRecord(pp->cfork, st));
+  LIST_CUDA(cudaStreamWaitEvent(pp->cp, pp->cfork, 0));
+  LIST_CUDA(cudaMemcpyAsync(base + p.raw_T, trans_mat_host, static_cast<size_t>(B) * 48, cudaMemcpyHostToDevice, pp->cp));
   const float* dmaps[LIST_MAX_MAPS];
   int cm = 0;
   for (int i = 0; i < n_maps; ++i) {
     const size_t bytes = static_cast<size_t>(B) * map_ch[i] * map_size_in[i] * map_size_in[i] * 4;
-    LIST_CUDA(cudaMemcpyAsync(base + p.raw_maps[i], maps_host[i], bytes, cudaMemcpyHostToDevice, st));
+    LIST_CUDA(cudaMemcpyAsync(base + p.raw_maps[i], maps_host[i], bytes, cudaMemcpyHostToDevice, pp->cp));
     dmaps[i] = reinterpret_cast<const float*>(base + p.raw_maps[i]);
     cm += map_ch[i];
   }
-  for (int l = 0; l < n_levels; ++l) {
-    const size_t bytes = static_cast<size_t>(B) * vol_ch[l] * vol_res[l] * vol_res[l] * vol_res[l] * 4;
-    LIST_CUDA(cudaMemcpyAsync(base + p.raw_vols[l], vols_host[l], bytes, cudaMemcpyHostToDevice, st));
-  }
-  LIST_CUDA(cudaMemcpyAsync(base + p.raw_T, trans_mat_host, static_cast<size_t>(B) * 48, cudaMemcpyHostToDevice, st));
-  int rc;
+  int order[LIST_MAX_LEVELS];
+  for (int l = 0; l < n_levels; ++l) order[l] = l;
+  auto vol_bytes = [&](int l) { return static_cast<size_t>(B) * vol_ch[l] * vol_res[l] * vol_res[l] * vol_res[l] * 4; };
+  for (int i = 1; i < n_levels; ++i)                                      // insertion sort: coarse levels first, then by size
+    for (int j = i; j > 0; --j) {
+      const int x = order[j - 1], y = order[j];
+      const bool sx = vol_res[x] <= 16, sy = vol_res[y] <= 16;
+      if ((sy && !sx) || (sx == sy && vol_bytes(y) < vol_bytes(x))) { order[j - 1] = y; order[j] = x; } else break;
+    }
+  int n_small = 0;
+  while (n_small < n_levels && vol_res[order[n_small]] <= 16) ++n_small;
+  for (int i = 0; i < n_small; ++i)
+    LIST_CUDA(cudaMemcpyAsync(base + p.raw_vols[order[i]], vols_host[order[i]], vol_bytes(order[i]), cudaMemcpyHostToDevice, pp->cp));
+  LIST_CUDA(cudaEventRecord(pp->small, pp->cp));
+  for (int i = n_small; i < n_levels; ++i)
+    LIST_CUDA(cudaMemcpyAsync(base + p.raw_vols[order[i]], vols_host[order[i]], vol_bytes(order[i]), cudaMemcpyHostToDevice, pp->cp));
+  LIST_CUDA(cudaEventRecord(pp->big, pp->cp));
+
+  LIST_CUDA(cudaStreamWaitEvent(st, pp->small, 0));
   if ((rc = list_prep_maps(dmaps, map_ch, map_size_in, n_maps, B, map_size, base + p.maps_cl, dtype, stream))) return rc;
   ListCtx ctx{};
   ctx.B = B;
@@ -667,18 +743,36 @@ int list_sdf_grid_host(const float* const* maps_host, const int32_t* map_ch, con
   ctx.maps = base + p.maps_cl;
   ctx.n_levels = n_levels;
   for (int l = 0; l < n_levels; ++l) {
-    if ((rc = list_prep_volume(reinterpret_cast<const float*>(base + p.raw_vols[l]), B, vol_ch[l], vol_res[l],
-                               base + p.vols_cl[l], dtype, stream)))
-      return rc;
     ctx.vol_res[l] = vol_res[l];
     ctx.vol_ch[l] = vol_ch[l];
     ctx.vols[l] = base + p.vols_cl[l];
   }
   ctx.trans_mat = reinterpret_cast<const float*>(base + p.raw_T);
+  auto prep_levels = [&](int i0, int i1, cudaStream_t s) -> int {
+    for (int i = i0; i < i1; ++i) {
+      const int l = order[i];
+      const int r2 = list_prep_volume(reinterpret_cast<const float*>(base + p.raw_vols[l]), B, vol_ch[l], vol_res[l],
+                                      base + p.vols_cl[l], dtype, s);
+      if (r2) return r2;
+    }
+    return LIST_OK;
+  };
+  if ((rc = prep_levels(0, n_small, st))) return rc;
+  struct Late { decltype(prep_levels)* f; int i0, i1; } late{&prep_levels, n_small, n_levels};
+  GridHooks hooks;
+  hooks.uploaded = pp->big;
+  hooks.late = [](void* u, cudaStream_t s) -> int { auto* l = static_cast<Late*>(u); return (*l->f)(l->i0, l->i1, s); };
+  hooks.user = &late;
+  hooks.sdf_host = sdf_host;
+  hooks.copy = pp->cp;
+  hooks.item = pp->item;
   float* dsdf = reinterpret_cast<float*>(base + p.sdf);
-  if ((rc = list_sdf_grid(&ctx, w_dev, res, bb_min, bb_max, begin, count, dsdf, sdf_scale, chunk_rows, base + p.ws, p.total - p.ws, stream)))
+  if ((rc = grid_impl(&ctx, w_dev, res, bb_min, bb_max, begin, count, dsdf, sdf_scale, chunk_rows, base + p.ws, p.total - p.ws,
+                      stream, &hooks)))
     return rc;
-  LIST_CUDA(cudaMemcpyAsync(sdf_host, dsdf, static_cast<size_t>(B) * count * 4, cudaMemcpyDeviceToHost, st));
+  // join: the caller's stream continues after the last download
+  LIST_CUDA(cudaEventRecord(pp->cdone, pp->cp));
+  LIST_CUDA(cudaStreamWaitEvent(st, pp->cdone, 0));
   return LIST_OK;
 }
 

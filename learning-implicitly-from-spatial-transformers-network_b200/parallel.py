@@ -59,9 +59,11 @@ def rebuild_from_gathered(gathered: torch.Tensor, per, fulls) -> None:
 class ShardedHostRunner:
     """End-to-end dense-grid evaluation from HOST buffers on `world` ranks (bench.py's e2e leg):
     pinned reference-layout per-image tensors -> device -> prep kernels -> this rank's shard of the grid -> pinned
-    host shard.  With one rank every tensor is uploaded whole.  With several, uploading the same 206 MB on every rank
-    would make the step PCIe-bound, so each rank uploads 1/world of every tensor and ONE all_gather over NVLink
-    rebuilds the full set on every GPU (the per-image tensors are replicated, the grid is what is sharded)."""
+    host shard.  With one rank this is the C-ABI host-buffer call (list_sdf_grid_host), which overlaps the upload of
+    the big volumes with the projection and the first chunk's addend gather, and every chunk's download with the next
+    chunk's kernels.  With several ranks, uploading the same 206 MB on every rank would make the step PCIe-bound, so
+    each rank uploads 1/world of every tensor and ONE all_gather over NVLink rebuilds the full set on every GPU (the
+    per-image tensors are replicated, the grid is what is sharded)."""
 
     def __init__(self, maps_host, vols_host, trans_host, weights, res: int, dtype="bf16", chunk_rows: int = 1048576,
                  group=None):
@@ -82,6 +84,12 @@ class ShardedHostRunner:
         total = res ** 3
         self.begin, self.count = shard_range(total, self.rank, self.world, align=res * res)
         self.chunk = max(1, min(chunk_rows, self.count))
+        self.single = None
+        if self.world == 1:
+            self.single = hotpath.HostGridRunner(maps_host, vols_host, trans_host, weights, res, self.begin, self.count,
+                                                 dtype, self.chunk)
+            self.h2d_bytes, self.d2h_bytes = self.single.h2d_bytes, self.single.d2h_bytes
+            return
         self.full = [torch.empty(t.shape, device=dev, dtype=torch.float32) for t in self.hosts]
         self.out_dev = torch.empty(trans_host.shape[0], self.count, device=dev, dtype=torch.float32)
         self.out_host = torch.empty(trans_host.shape[0], self.count, dtype=torch.float32).pin_memory()
@@ -96,19 +104,17 @@ class ShardedHostRunner:
 
     def run(self, sdf_scale: float = 1.0) -> torch.Tensor:
         hp = self.hotpath
-        if self.world == 1:
-            for d, h in zip(self.full, self.hosts):
-                d.copy_(h, non_blocking=True)
-        else:
-            off = 0
-            for h, p in zip(self.hosts, self.per):
-                flat = h.view(-1)
-                lo, hi = slice_bounds(flat.numel(), p, self.rank)
-                if hi > lo:
-                    self.mine[off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
-                off += p
-            dist.all_gather_into_tensor(self.gathered.view(-1), self.mine, group=self.group)
-            rebuild_from_gathered(self.gathered, self.per, self.full)
+        if self.single is not None:
+            return self.single.run(sdf_scale)
+        off = 0
+        for h, p in zip(self.hosts, self.per):
+            flat = h.view(-1)
+            lo, hi = slice_bounds(flat.numel(), p, self.rank)
+            if hi > lo:
+                self.mine[off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
+            off += p
+        dist.all_gather_into_tensor(self.gathered.view(-1), self.mine, group=self.group)
+        rebuild_from_gathered(self.gathered, self.per, self.full)
         maps, vols, T = self.full[:self.n_maps], self.full[self.n_maps:-1], self.full[-1]
         ctx = hp.prepare_context(maps, vols, T, self.dtype)
         if self.workspace is None:

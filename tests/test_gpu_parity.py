@@ -399,6 +399,40 @@ def test_host_buffer_entry_points_equal_the_resident_path():
             assert torch.equal(out, whole.cpu())
 
 
+def test_host_buffer_call_overlaps_transfers_without_races():
+    """list_sdf_grid_host uploads the big volumes while the projection / first addend gather run and downloads every
+    chunk behind the next one's kernels.  Back-to-back calls on the same scratch with DIFFERENT inputs, two images, one
+    and many chunks: each result must equal the resident path of its own inputs (a stale or half-uploaded tensor, or a
+    download racing the next call's kernels, would show up here)."""
+    res = 40
+    pin = lambda t: t.contiguous().pin_memory()
+    sets = [synth.make_inputs(seed=50 + i, B=2, N=8, size="small", trans="camera") for i in range(3)]
+    for mode in ("bf16", "fp32"):
+        for chunk in (4096, res ** 3):
+            want = []
+            _, kw = ctx_and_weights(sets[0].to(DEV), mode)             # one set of weights for every call
+            for inp in sets:
+                g = inp.to(DEV)
+                ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, mode)
+                want.append(hotpath.grid_sdf(ctx, kw, res, 0, res ** 3, sdf_scale=2.0, chunk_rows=chunk).cpu())
+            torch.cuda.synchronize()
+            # one runner: same pinned host tensors and device scratch, refilled between calls
+            maps, vols, T = [pin(m) for m in sets[0].maps], [pin(v) for v in sets[0].vols], pin(sets[0].trans_mat)
+            runner = hotpath.HostGridRunner(maps, vols, T, kw, res, 0, res ** 3, mode, chunk)
+            for i, inp in enumerate(sets):
+                for dst, src in zip([*maps, *vols, T], [*inp.maps, *inp.vols, inp.trans_mat]):
+                    dst.copy_(src)
+                got = runner.run(2.0)                      # no sync between enqueue and the next host-side refill ...
+                torch.cuda.synchronize()                   # ... except this one: the host tensors are reused
+                assert torch.equal(got, want[i]), (mode, chunk, i)
+            # two calls enqueued back to back without a host sync in between (same inputs): the second must not disturb
+            # the first one's downloads, and both leave the same values
+            runner.run(2.0)
+            got = runner.run(2.0)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want[-1]), (mode, chunk, "back-to-back")
+
+
 # ------------------------------------------------------------------ SURVEY.md §8d parity gates at the configured sizes
 def _camera_inputs():
     return synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")
