@@ -176,5 +176,11 @@ __device__ __forceinline__ float linspace_f32(int i, int res, double lo, double 
   const double v = (i == res - 1) ? hi : __dadd_rn(__dmul_rn(static_cast<double>(i), step), lo);
   return static_cast<float>(v);
 }
+// same value with the (double) step precomputed on the host: (hi - lo) / (res - 1) is an IEEE division on both sides
+__device__ __forceinline__ float linspace_f32_step(int i, int res, double lo, double hi, double step) {
+  if (res == 1) return static_cast<float>(lo);
+  const double v = (i == res - 1) ? hi : __dadd_rn(__dmul_rn(static_cast<double>(i), step), lo);
+  return static_cast<float>(v);
+}
 
 }  // namespace list

@@ -42,41 +42,47 @@ namespace hoist {
 // point range [begin, end).  Everything a tile computes is therefore a function of absolute grid positions
 // only, which is what makes any chunking / sharding of the grid bit-identical.
 struct TileMap {
-  int64_t line0;                    // first z-line (flat index / res) touched by [begin, end)
+  int64_t line0;                    // first z-line (flat index / res) touched by [begin, end); < res^2 <= 2^22
   int64_t begin, end;               // flat grid range of this launch
   int segs;                         // tiles per z-line
-  int kPz;                          // steps per tile
+  int kPz, lg_kpz;                  // steps per tile (a power of two)
   int res;
-  double bb_min, bb_max;
+  double bb_min, bb_max, step;      // step = (bb_max - bb_min) / (res - 1), the linspace increment
 };
 
 struct TileSpan {
   int64_t g_tile0;                  // flat grid index of step 0
+  int gz0;                          // its position on the z-line
   int s_lo, s_hi;                   // steps of the tile inside [begin, end)
   float qy, qz;                     // swapped/scaled query components 1 (-> H) and 2 (-> D), constant over the tile
 };
 
+// 32-bit index arithmetic only (64-bit divisions cost ~100 instructions each and every thread of a tile runs this)
 __device__ __forceinline__ bool tile_span(const TileMap& m, unsigned tile, TileSpan& t) {
-  const int64_t line = m.line0 + tile / m.segs;
-  const int gz0 = static_cast<int>(tile % m.segs) * m.kPz;
-  t.g_tile0 = line * m.res + gz0;
-  const int full = min(m.kPz, m.res - gz0);
+  const unsigned lrel = tile / static_cast<unsigned>(m.segs);
+  const unsigned seg = tile - lrel * static_cast<unsigned>(m.segs);
+  const unsigned line = static_cast<unsigned>(m.line0) + lrel;
+  const unsigned lz = line / static_cast<unsigned>(m.res), ly = line - lz * static_cast<unsigned>(m.res);
+  t.gz0 = static_cast<int>(seg) << m.lg_kpz;
+  t.g_tile0 = static_cast<int64_t>(line) * m.res + t.gz0;
+  const int full = min(m.kPz, m.res - t.gz0);
   t.s_lo = static_cast<int>(max(static_cast<int64_t>(0), m.begin - t.g_tile0));
   t.s_hi = static_cast<int>(min(static_cast<int64_t>(full), m.end - t.g_tile0));
   // reference utils.py:84-95 (x slowest, z fastest) and models.py:91-92 ([2,1,0] swap, *2)
-  t.qy = linspace_f32(static_cast<int>(line % m.res), m.res, m.bb_min, m.bb_max) * 2.0f;
-  t.qz = linspace_f32(static_cast<int>(line / m.res), m.res, m.bb_min, m.bb_max) * 2.0f;
+  t.qy = linspace_f32_step(static_cast<int>(ly), m.res, m.bb_min, m.bb_max, m.step) * 2.0f;
+  t.qz = linspace_f32_step(static_cast<int>(lz), m.res, m.bb_min, m.bb_max, m.step) * 2.0f;
   return t.s_lo < t.s_hi;
 }
 __device__ __forceinline__ float step_q0(const TileMap& m, const TileSpan& t, int s) {
-  return linspace_f32(static_cast<int>(t.g_tile0 % m.res) + s, m.res, m.bb_min, m.bb_max) * 2.0f;
+  return linspace_f32_step(t.gz0 + s, m.res, m.bb_min, m.bb_max, m.step) * 2.0f;
 }
 
 constexpr int kTile = 128;          // max steps per tile (rest kernel)
 #ifndef LIST_ADD_TILE
 #define LIST_ADD_TILE 128
 #endif
-constexpr int kAddTile = LIST_ADD_TILE;   // steps per tile of the addend kernel (multiple of 128)
+constexpr int kAddTile = LIST_ADD_TILE;   // steps per tile of the addend kernel (a power of two >= 128)
+static_assert(kAddTile >= 128 && (kAddTile & (kAddTile - 1)) == 0, "tile decoding uses shifts");
 constexpr int kN0 = 512;            // fc_0 width == addend channels
 constexpr int kRestThreads = 256;
 constexpr int kRestLevels = 4;      // non-hoisted levels (vector ones first)
@@ -106,6 +112,9 @@ struct RestParams {
   int tab_floats;                   // floats of all column tables (the per-step tables follow)
   int nvl, nsl;                     // vector levels [0, nvl), scalar levels [nvl, nvl + nsl)
   int lwarp0[kRestLevels + 1];      // phase L: warps [lwarp0[i], lwarp0[i+1]) work on vector level i
+  // division-free index decoding of the vector levels (ncv = C / 8 is a power of two; fast_div reciprocals)
+  int lg_ncv[kRestLevels], g_lanes[kRestLevels], l_nblk[kRestLevels];
+  float inv_combos[kRestLevels], inv_lnblk[kRestLevels];
   int nvec;                         // 16-byte items per row of the vector levels
   int g_items;                      // phase-G items of the vector levels
   int tail0, xyz_off, k_h;          // tail region [tail0, k_h): scalar levels, q, zero pad
@@ -432,7 +441,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   }
   __syncthreads();
   for (int i = tid; i < nlev * 3 * kPz; i += kRestThreads) {
-    const int s = i % kPz, lc = i / kPz;
+    const int s = i & (kPz - 1), lc = i >> p.tm.lg_kpz;
     const int li = lc / 3, cls = lc % 3;
     int rel = 0;
     float w1 = 0.f;
@@ -451,10 +460,10 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     for (int li = 0; li < p.nvl; ++li) {
       const int C = p.C[li], ncv = C >> 3, cm = p.cells_max[li];
       const int combos = LIST_NUM_DISP * ncv;                           // <= kMaxVec <= kRestThreads / 2
-      const int lanes = kRestThreads / combos;
-      const int combo = tid % combos, lane0 = tid / combos;
+      const int lanes = p.g_lanes[li];                                  // kRestThreads / combos
+      const int lane0 = fast_div(tid, p.inv_combos[li]), combo = tid - lane0 * combos;
       if (lane0 >= lanes) continue;
-      const int d = combo / ncv, cvv = combo - d * ncv;
+      const int d = combo >> p.lg_ncv[li], cvv = combo - (d << p.lg_ncv[li]);
       const int cls = shift_class(d);
       const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
       const Corner c0 = cor[0], c1 = cor[1], c2 = cor[2], c3 = cor[3];
@@ -509,11 +518,12 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     const int nvec = LIST_NUM_DISP * ncv;
     const int T = (p.lwarp0[li + 1] - p.lwarp0[li]) * 32;               // threads of this level
     const int lt = tid - p.lwarp0[li] * 32;
-    const int nblk = max(1, T / nvec);
-    const int per = (nsteps + nblk - 1) / nblk;
+    const int nblk = p.l_nblk[li];                                      // max(1, T / nvec)
+    const int per = fast_div(nsteps + nblk - 1, p.inv_lnblk[li]);
+    const float inv_nvec = p.inv_combos[li];                            // nvec == combos of the level
     for (int it = lt; it < nvec * nblk; it += T) {
-      const int v = it % nvec, blk = it / nvec;
-      const int d = v / ncv, cvv = v - d * ncv;
+      const int blk = fast_div(it, inv_nvec), v = it - blk * nvec;
+      const int d = v >> p.lg_ncv[li], cvv = v - (d << p.lg_ncv[li]);
       const int cls = shift_class(d);
       const int sr0 = blk * per, sr1 = min(nsteps, sr0 + per);
       const unsigned char* __restrict__ rels = s_rel + (li * 3 + cls) * kPz + t.s_lo;
@@ -689,6 +699,17 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
     while (used < nw) { int k = 0; for (int i = 1; i < r.nvl; ++i) if (cost[i] / w[i] > cost[k] / w[k]) k = i; ++w[k]; ++used; }
     r.lwarp0[0] = 0;
     for (int i = 0; i < r.nvl; ++i) r.lwarp0[i + 1] = r.lwarp0[i] + w[i];
+    for (int i = 0; i < r.nvl; ++i) {
+      const int ncv = r.C[i] / 8, combos = LIST_NUM_DISP * ncv;
+      int lg = 0;
+      while ((1 << lg) < ncv) ++lg;
+      r.lg_ncv[i] = lg;
+      r.g_lanes[i] = kRestThreads / combos;
+      r.inv_combos[i] = 1.0f / static_cast<float>(combos);
+      const int nblk = (w[i] * 32) / combos > 1 ? (w[i] * 32) / combos : 1;
+      r.l_nblk[i] = nblk;
+      r.inv_lnblk[i] = 1.0f / static_cast<float>(nblk);
+    }
   }
   r.tail0 = tail0 - shift;
   r.xyz_off = lay.xyz_off - shift;
@@ -733,10 +754,13 @@ static void fill_tilemap(TileMap* tm, int res, double bb_min, double bb_max, int
   tm->begin = begin;
   tm->end = begin + count;
   tm->kPz = kpz;
+  tm->lg_kpz = 0;
+  while ((1 << tm->lg_kpz) < kpz) ++tm->lg_kpz;
   tm->segs = (res + kpz - 1) / kpz;
   tm->res = res;
   tm->bb_min = bb_min;
   tm->bb_max = bb_max;
+  tm->step = res > 1 ? (bb_max - bb_min) / static_cast<double>(res - 1) : 0.0;
 }
 static unsigned tile_count(const TileMap& tm) {
   const int64_t lines = (tm.end - 1) / tm.res - tm.line0 + 1;
