@@ -204,7 +204,12 @@ LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res
 
 /* Same call with HOST buffers end to end (the e2e path of bench.py): reference-layout fp32
  * per-image tensors in (pinned) host memory -> H2D -> prep -> grid evaluation -> D2H of the
- * SDF grid.  dev_scratch is a caller-owned DEVICE arena of >= list_sdf_grid_host_bytes(). */
+ * SDF grid.  dev_scratch is a caller-owned DEVICE arena of >= list_sdf_grid_host_bytes().
+ * Transfers run on an internal copy stream, forked from and joined to `stream`: the fine
+ * volumes upload while the projection and the first chunk's addend gather run, every chunk's
+ * SDF values download behind the next chunk's kernels.  The host buffers must
+ * stay untouched until the work enqueued on `stream` by this call is done; pinned memory is
+ * needed for the overlap, not for correctness. */
 LIST_API size_t list_sdf_grid_host_bytes(const int32_t* map_ch, const int32_t* map_size_in, int32_t n_maps,
                                 int32_t map_size, int32_t n_levels, const int32_t* vol_ch,
                                 const int32_t* vol_res, int32_t B, int32_t dtype, int64_t count,
