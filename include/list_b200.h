@@ -202,6 +202,19 @@ LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res
                   double bb_max, int64_t begin, int64_t count, float* sdf, float sdf_scale,
                   int64_t chunk_rows, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Staged variant for callers that are still producing the fine volumes (upload, all-gather ...) on another
+ * stream: every level l with late_vols_ncdhw[l] != NULL is NOT yet valid in ctx->vols[l]; the call waits for
+ * late_event (a cudaEvent_t recorded after the producer's last write, or NULL) right before its first kernel
+ * that reads such a level -- the projection and the first chunk's addend gather run before that -- and prepares
+ * the level itself (list_prep_volume from the reference-layout fp32 DEVICE tensor late_vols_ncdhw[l] into
+ * ctx->vols[l]).  sdf_host (pinned host memory, [B][count], or NULL) additionally receives every chunk's values
+ * behind the next chunk's kernels.  Levels with R <= 16 and C % 64 == 0 may be read by the projection and cannot
+ * be late (LIST_EINVAL).  late_vols_ncdhw == NULL and sdf_host == NULL: same as list_sdf_grid. */
+LIST_API int list_sdf_grid_late(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min,
+                       double bb_max, int64_t begin, int64_t count, float* sdf, float sdf_scale,
+                       int64_t chunk_rows, void* workspace, size_t workspace_bytes, void* stream,
+                       void* late_event, const float* const* late_vols_ncdhw, float* sdf_host);
+
 /* Same call with HOST buffers end to end (the e2e path of bench.py): reference-layout fp32
  * per-image tensors in (pinned) host memory -> H2D -> prep -> grid evaluation -> D2H of the
  * SDF grid.  dev_scratch is a caller-owned DEVICE arena of >= list_sdf_grid_host_bytes().

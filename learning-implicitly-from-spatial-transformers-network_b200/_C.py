@@ -82,6 +82,8 @@ SIGNATURES = {
     "list_sdf_workspace_bytes": (_sz, [_P(ListCtx), _P(ListWeights), _i64]),
     "list_sdf_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _i64, _vp, _f32, _i64, _vp, _sz, _vp]),
     "list_sdf_grid": (C.c_int, [_P(ListCtx), _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _vp, _f32, _i64, _vp, _sz, _vp]),
+    "list_sdf_grid_late": (C.c_int, [_P(ListCtx), _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _vp, _f32, _i64, _vp, _sz, _vp,
+                                     _vp, _P(_vp), _vp]),
     "list_sdf_grid_host_bytes": (_sz, [_P(_i32), _P(_i32), _i32, _i32, _i32, _P(_i32), _P(_i32), _i32, _i32, _i64, _i64]),
     "list_sdf_grid_host": (C.c_int, [_P(_vp), _P(_i32), _P(_i32), _i32, _i32, _P(_vp), _i32, _P(_i32), _P(_i32), _vp,
                                      _i32, _i32, _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _f32, _i64, _vp, _vp,

@@ -181,7 +181,7 @@ struct GridHooks {
 };
 static int hook_late(const GridHooks* h, cudaStream_t s) {
   if (!h || !h->late) return LIST_OK;
-  LIST_CUDA(cudaStreamWaitEvent(s, h->uploaded, 0));
+  if (h->uploaded) LIST_CUDA(cudaStreamWaitEvent(s, h->uploaded, 0));
   return h->late(h->user, s);
 }
 // values [off, off + n) of the SDF buffer are final once the work enqueued on `s` so far is done
@@ -633,6 +633,51 @@ int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double 
                   void* stream) {
   return grid_impl(ctx, w, res, bb_min, bb_max, begin, count, sdf, sdf_scale, chunk_rows, workspace, workspace_bytes, stream,
                    nullptr);
+}
+
+// Device-resident variant of the staged evaluation: the caller has the coarse tensors prepared in `ctx` already and is
+// still producing (uploading, all-gathering ...) the reference-layout volumes of the other levels on another stream.
+int list_sdf_grid_late(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
+                       int64_t count, float* sdf, float sdf_scale, int64_t chunk_rows, void* workspace, size_t workspace_bytes,
+                       void* stream, void* late_event, const float* const* late_vols_ncdhw, float* sdf_host) {
+  LIST_CHECK_ARG(ctx != nullptr, "list_sdf_grid_late: ctx is NULL");
+  Pipe* pp = nullptr;
+  int rc;
+  if ((rc = get_pipe(&pp))) return rc;
+  struct Late { const ListCtx* ctx; const float* const* raw; } late{ctx, late_vols_ncdhw};
+  GridHooks hooks;
+  if (late_vols_ncdhw) {
+    LIST_CHECK_ARG(w != nullptr && ctx->n_levels >= 1 && ctx->n_levels <= LIST_MAX_LEVELS, "list_sdf_grid_late: bad ctx / weights");
+    hoist::Plan pl;                                     // the projection runs first and reads the hoisted levels
+    if (ctx->dtype == LIST_BF16 && hoist_enabled() && hoist::make_plan(ctx, w, &pl) == LIST_OK)
+      for (int h = 0; h < pl.nh; ++h)
+        LIST_CHECK_ARG(late_vols_ncdhw[pl.lev[h]] == nullptr,
+                       "list_sdf_grid_late: level %d (R <= 16, C %% 64 == 0) is read by the projection and cannot be late", pl.lev[h]);
+    hooks.uploaded = static_cast<cudaEvent_t>(late_event);
+    hooks.user = &late;
+    hooks.late = [](void* u, cudaStream_t s) -> int {
+      auto* l = static_cast<Late*>(u);
+      for (int i = 0; i < l->ctx->n_levels; ++i) {
+        if (!l->raw[i]) continue;
+        const int r2 = list_prep_volume(l->raw[i], l->ctx->B, l->ctx->vol_ch[i], l->ctx->vol_res[i],
+                                        const_cast<void*>(l->ctx->vols[i]), l->ctx->dtype, s);
+        if (r2) return r2;
+      }
+      return LIST_OK;
+    };
+  }
+  hooks.sdf_host = sdf_host;
+  hooks.copy = pp->cp;
+  hooks.item = pp->item;
+  if ((rc = grid_impl(ctx, w, res, bb_min, bb_max, begin, count, sdf, sdf_scale, chunk_rows, workspace, workspace_bytes, stream,
+                      &hooks)))
+    return rc;
+  if (sdf_host) {                                       // join: the caller's stream continues after the last download
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    LIST_CUDA(cudaEventRecord(pp->cdone, pp->cp));
+    LIST_CUDA(cudaStreamWaitEvent(st, pp->cdone, 0));
+  }
+  return LIST_OK;
 }
 
 // ---- host-buffer variant -----------------------------------------------------------------

@@ -112,9 +112,10 @@ class HotPathContext:
 
 
 def prepare_context(maps: Sequence[torch.Tensor], vols: Sequence[torch.Tensor], trans_mat: torch.Tensor,
-                    dtype="fp32", map_size: int = MAP_SIZE) -> HotPathContext:
+                    dtype="fp32", map_size: int = MAP_SIZE, skip_levels: Sequence[int] = ()) -> HotPathContext:
     """Once per image (hoists reference modules.py:25-35 out of the chunk loop): NCHW maps ->
-    upsampled channels-last, NCDHW volumes -> channels-last, optional bf16."""
+    upsampled channels-last, NCDHW volumes -> channels-last, optional bf16.  Levels in `skip_levels` only get their
+    buffer; grid_sdf_late fills them (staged evaluation)."""
     code = dtype_code(dtype)
     dev = _require_cuda(*maps, *vols, trans_mat)
     lib = _C.lib()
@@ -138,10 +139,11 @@ def prepare_context(maps: Sequence[torch.Tensor], vols: Sequence[torch.Tensor], 
                                     _C.i32_array([m.shape[2] for m in maps]),
                                     len(maps), B, map_size, maps_cl.data_ptr(), code, _stream()), "list_prep_maps")
         vols_cl = []
-        for v in vols:
+        for l, v in enumerate(vols):
             out = torch.empty(B, v.shape[2], v.shape[3], v.shape[4], v.shape[1], device=dev, dtype=tdt)
-            _C.check(lib.list_prep_volume(v.data_ptr(), B, v.shape[1], v.shape[2], out.data_ptr(), code, _stream()),
-                     "list_prep_volume")
+            if l not in skip_levels:
+                _C.check(lib.list_prep_volume(v.data_ptr(), B, v.shape[1], v.shape[2], out.data_ptr(), code, _stream()),
+                         "list_prep_volume")
             vols_cl.append(out)
     return HotPathContext(maps_cl, vols_cl, trans_mat.detach().to(torch.float32).contiguous(), code)
 
@@ -345,6 +347,33 @@ def grid_sdf(ctx: HotPathContext, weights: KernelWeights, res: int, begin: int =
         _C.check(_C.lib().list_sdf_grid(C.byref(cs), C.byref(wsn), res, bb_min, bb_max, begin, count, out.data_ptr(),
                                         float(sdf_scale), chunk_rows, ws.data_ptr(), ws.numel(), _stream()),
                  "list_sdf_grid")
+    return out
+
+
+def grid_sdf_late(ctx: HotPathContext, weights: KernelWeights, res: int, begin: int, count: int, sdf_scale: float,
+                  chunk_rows: int, out: torch.Tensor, workspace: torch.Tensor, late_event: Optional[torch.cuda.Event],
+                  late_vols: Sequence[Optional[torch.Tensor]], out_host: Optional[torch.Tensor] = None,
+                  bb_min: float = -0.5, bb_max: float = 0.5) -> torch.Tensor:
+    """grid_sdf for a context whose fine levels are still being produced on another stream (list_sdf_grid_late):
+    late_vols[l] is the reference-layout fp32 device tensor of a level prepare_context skipped (None for the others),
+    late_event was recorded after its producer's last write.  out_host (pinned) receives the values chunk by chunk."""
+    dev = _require_cuda(ctx.maps_cl, weights.w0)
+    if count == 0:
+        return out
+    if out_host is not None and (not out_host.is_pinned() or out_host.numel() != out.numel() or out_host.dtype != torch.float32):
+        raise ValueError("out_host must be a pinned fp32 tensor of B*count elements")
+    for l, v in enumerate(late_vols):
+        if v is not None and (not v.is_cuda or v.dtype != torch.float32 or not v.is_contiguous()
+                              or tuple(v.shape[2:]) != tuple(ctx.vols_cl[l].shape[1:4])):
+            raise ValueError(f"late volume {l}: expected a contiguous fp32 NCDHW device tensor matching the context")
+    cs, wsn = ctx.struct(), weights.struct()
+    raw = _C.ptr_array([0 if v is None else v.data_ptr() for v in late_vols])
+    ev = None if late_event is None else late_event.cuda_event
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().list_sdf_grid_late(C.byref(cs), C.byref(wsn), res, bb_min, bb_max, begin, count, out.data_ptr(),
+                                             float(sdf_scale), max(1, min(chunk_rows, count)), workspace.data_ptr(),
+                                             workspace.numel(), _stream(), ev, raw,
+                                             None if out_host is None else out_host.data_ptr()), "list_sdf_grid_late")
     return out
 
 

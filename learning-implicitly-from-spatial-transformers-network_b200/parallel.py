@@ -94,9 +94,22 @@ class ShardedHostRunner:
         self.out_dev = torch.empty(trans_host.shape[0], self.count, device=dev, dtype=torch.float32)
         self.out_host = torch.empty(trans_host.shape[0], self.count, dtype=torch.float32).pin_memory()
         self.per = [-(-t.numel() // self.world) for t in self.hosts]           # elements of every rank's slice
-        if self.world > 1:
-            self.mine = torch.zeros(sum(self.per), device=dev, dtype=torch.float32)
-            self.gathered = torch.empty(self.world, sum(self.per), device=dev, dtype=torch.float32)
+        # Two stages (same idea as list_sdf_grid_host): the coarse tensors -- maps, levels with R <= 16, T,
+        # all the projection and the first addend gather read -- are uploaded and all-gathered first; the fine levels
+        # follow on a side stream while those kernels run, and list_sdf_grid_late prepares them when they are there.
+        n_lev = len(vols_host)
+        self.late_levels = [l for l in range(n_lev) if vols_host[l].shape[2] > 16]
+        late_idx = {self.n_maps + l for l in self.late_levels}
+        self.stages = []
+        for idx in ([i for i in range(len(self.hosts)) if i not in late_idx], sorted(late_idx)):
+            if not idx:
+                continue
+            per = [self.per[i] for i in idx]
+            self.stages.append({"idx": idx, "per": per,
+                                "mine": torch.zeros(sum(per), device=dev, dtype=torch.float32),
+                                "gathered": torch.empty(self.world, sum(per), device=dev, dtype=torch.float32),
+                                "event": torch.cuda.Event()})
+        self.side = torch.cuda.Stream(device=dev)
         self.h2d_bytes = sum((slice_bounds(t.numel(), p, self.rank)[1] - slice_bounds(t.numel(), p, self.rank)[0]) * 4
                              for t, p in zip(self.hosts, self.per))
         self.d2h_bytes = self.out_host.numel() * 4
@@ -106,20 +119,27 @@ class ShardedHostRunner:
         hp = self.hotpath
         if self.single is not None:
             return self.single.run(sdf_scale)
-        off = 0
-        for h, p in zip(self.hosts, self.per):
-            flat = h.view(-1)
-            lo, hi = slice_bounds(flat.numel(), p, self.rank)
-            if hi > lo:
-                self.mine[off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
-            off += p
-        dist.all_gather_into_tensor(self.gathered.view(-1), self.mine, group=self.group)
-        rebuild_from_gathered(self.gathered, self.per, self.full)
+        main = torch.cuda.current_stream(self.dev)
+        self.side.wait_stream(main)                      # the previous call's readers of self.full are done
+        with torch.cuda.stream(self.side):
+            for st in self.stages:
+                off = 0
+                for i, p in zip(st["idx"], st["per"]):
+                    flat = self.hosts[i].view(-1)
+                    lo, hi = slice_bounds(flat.numel(), p, self.rank)
+                    if hi > lo:
+                        st["mine"][off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
+                    off += p
+                dist.all_gather_into_tensor(st["gathered"].view(-1), st["mine"], group=self.group)
+                rebuild_from_gathered(st["gathered"], st["per"], [self.full[i] for i in st["idx"]])
+                st["event"].record(self.side)
+        main.wait_event(self.stages[0]["event"])
         maps, vols, T = self.full[:self.n_maps], self.full[self.n_maps:-1], self.full[-1]
-        ctx = hp.prepare_context(maps, vols, T, self.dtype)
+        staged = len(self.stages) > 1
+        ctx = hp.prepare_context(maps, vols, T, self.dtype, skip_levels=self.late_levels if staged else ())
         if self.workspace is None:
             self.workspace = hp._workspace(ctx.struct(), self.weights.struct(), self.chunk, self.dev)
-        hp.grid_sdf(ctx, self.weights, self.res, self.begin, self.count, sdf_scale, self.chunk, out=self.out_dev,
-                    workspace=self.workspace)
-        self.out_host.copy_(self.out_dev, non_blocking=True)
+        late = [vols[l] if (staged and l in self.late_levels) else None for l in range(len(vols))]
+        hp.grid_sdf_late(ctx, self.weights, self.res, self.begin, self.count, sdf_scale, self.chunk, self.out_dev,
+                         self.workspace, self.stages[-1]["event"] if staged else None, late, out_host=self.out_host)
         return self.out_host

@@ -433,6 +433,50 @@ def test_host_buffer_call_overlaps_transfers_without_races():
             assert torch.equal(got, want[-1]), (mode, chunk, "back-to-back")
 
 
+def test_staged_grid_call_prepares_late_levels_itself():
+    """list_sdf_grid_late (the multi-rank e2e leg): levels that are still being produced on another stream when the
+    call is made -- here: copied from pinned host memory behind a long sleep kernel -- are waited for and prepared by
+    the call; the context's buffers of those levels hold NaN until then, so a premature read cannot go unnoticed.  The
+    pinned host copy of the result arrives chunk by chunk.  Bit-identical to the plain call."""
+    inp = synth.make_inputs(seed=61, B=2, N=8, size="small", trans="camera")
+    g = inp.to(DEV)
+    res, begin, count = 40, 40 * 40 * 2, 40 * 40 * 30
+    late_levels = [l for l, v in enumerate(inp.vols) if v.shape[1] % 64 != 0]          # never read by the projection
+    assert late_levels
+    side = torch.cuda.Stream(device=DEV)
+    for mode in ("bf16", "fp32"):
+        ctx, kw = ctx_and_weights(g, mode)
+        want = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=3.0, chunk_rows=8192).cpu()
+        for chunk in (8192, count):
+            ctx2 = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, mode, skip_levels=late_levels)
+            raw = [None] * len(inp.vols)
+            pinned = {l: inp.vols[l].contiguous().pin_memory() for l in late_levels}
+            for l in late_levels:
+                ctx2.vols_cl[l].fill_(float("nan"))
+                raw[l] = torch.full_like(g.vols[l], float("nan"))
+            ws = hotpath._workspace(ctx2.struct(), kw.struct(), min(chunk, count), DEV)
+            out = torch.empty(2, count, device=DEV, dtype=torch.float32)
+            out_host = torch.zeros(2, count, dtype=torch.float32).pin_memory()
+            ev = torch.cuda.Event()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                torch.cuda._sleep(200_000_000)                                          # ~0.1 s: the call is enqueued long before
+                for l in late_levels:
+                    raw[l].copy_(pinned[l], non_blocking=True)
+                ev.record(side)
+            hotpath.grid_sdf_late(ctx2, kw, res, begin, count, 3.0, chunk, out, ws, ev, raw, out_host=out_host)
+            torch.cuda.synchronize()
+            assert torch.equal(out.cpu(), want), (mode, chunk)
+            assert torch.equal(out_host, want), (mode, chunk, "host copy")
+    # a level the projection reads cannot be late
+    ctx, kw = ctx_and_weights(g, "bf16")
+    hoisted = [l for l, v in enumerate(inp.vols) if v.shape[1] % 64 == 0]
+    raw = [g.vols[l] if l == hoisted[-1] else None for l in range(len(inp.vols))]
+    ws = hotpath._workspace(ctx.struct(), kw.struct(), 8192, DEV)
+    with pytest.raises(RuntimeError, match="cannot be late"):
+        hotpath.grid_sdf_late(ctx, kw, res, 0, 8192, 1.0, 8192, torch.empty(2, 8192, device=DEV), ws, None, raw)
+
+
 # ------------------------------------------------------------------ SURVEY.md §8d parity gates at the configured sizes
 def _camera_inputs():
     return synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")
