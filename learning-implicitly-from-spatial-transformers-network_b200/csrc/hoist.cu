@@ -15,7 +15,7 @@
 // in real arithmetic.  The fp32 parity path is untouched.
 //
 // Kernels here:
-//   hoist_addend_kernel  per 64-point tile of the grid, 64 threads, thread = 8 of the 512 addend channels:
+//   hoist_addend_kernel  per tile (z-line, segment of 128 steps), 128 threads, thread = 4 of the 512 addend channels:
 //                        walks the z-run with the separable scheme of gather_grid.cu -- bilinear taps of the
 //                        projected map (cell cache) + for each hoisted level the three W-shift classes
 //                        {d=0,3,4,5,6}, {d=1}, {d=2} of the displacement table (modules.py:205-212): the five
