@@ -56,6 +56,30 @@ def rebuild_from_gathered(gathered: torch.Tensor, per, fulls) -> None:
         off += p
 
 
+def upload_stages(vol_res, n_maps: int, n_tensors: int):
+    """Index lists (into [*maps, *vols, T]) of the two upload stages of the staged end-to-end path: everything the
+    projection and the first addend gather read (maps, levels with R <= 16, T), then the fine levels.  Returns
+    (stages, late_levels); a stage is dropped if empty."""
+    late_levels = [l for l, r in enumerate(vol_res) if r > 16]
+    late_idx = {n_maps + l for l in late_levels}
+    stages = [[i for i in range(n_tensors) if i not in late_idx], sorted(late_idx)]
+    return [st for st in stages if st], late_levels
+
+
+def gather_stage(hosts, idx, per, mine: torch.Tensor, gathered: torch.Tensor, fulls, rank: int, group=None) -> None:
+    """One upload stage: this rank's 1/world slice of every tensor in `idx` -> `mine` (device), ONE all_gather,
+    reassembly into fulls[i].  Device agnostic (the gloo tests run it on the CPU)."""
+    off = 0
+    for i, p in zip(idx, per):
+        flat = hosts[i].view(-1)
+        lo, hi = slice_bounds(flat.numel(), p, rank)
+        if hi > lo:
+            mine[off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
+        off += p
+    dist.all_gather_into_tensor(gathered.view(-1), mine, group=group)
+    rebuild_from_gathered(gathered, per, [fulls[i] for i in idx])
+
+
 class ShardedHostRunner:
     """End-to-end dense-grid evaluation from HOST buffers on `world` ranks (bench.py's e2e leg):
     pinned reference-layout per-image tensors -> device -> prep kernels -> this rank's shard of the grid -> pinned
@@ -97,13 +121,9 @@ class ShardedHostRunner:
         # Two stages (same idea as list_sdf_grid_host): the coarse tensors -- maps, levels with R <= 16, T,
         # all the projection and the first addend gather read -- are uploaded and all-gathered first; the fine levels
         # follow on a side stream while those kernels run, and list_sdf_grid_late prepares them when they are there.
-        n_lev = len(vols_host)
-        self.late_levels = [l for l in range(n_lev) if vols_host[l].shape[2] > 16]
-        late_idx = {self.n_maps + l for l in self.late_levels}
+        stage_idx, self.late_levels = upload_stages([v.shape[2] for v in vols_host], self.n_maps, len(self.hosts))
         self.stages = []
-        for idx in ([i for i in range(len(self.hosts)) if i not in late_idx], sorted(late_idx)):
-            if not idx:
-                continue
+        for idx in stage_idx:
             per = [self.per[i] for i in idx]
             self.stages.append({"idx": idx, "per": per,
                                 "mine": torch.zeros(sum(per), device=dev, dtype=torch.float32),
@@ -123,15 +143,7 @@ class ShardedHostRunner:
         self.side.wait_stream(main)                      # the previous call's readers of self.full are done
         with torch.cuda.stream(self.side):
             for st in self.stages:
-                off = 0
-                for i, p in zip(st["idx"], st["per"]):
-                    flat = self.hosts[i].view(-1)
-                    lo, hi = slice_bounds(flat.numel(), p, self.rank)
-                    if hi > lo:
-                        st["mine"][off:off + hi - lo].copy_(flat[lo:hi], non_blocking=True)
-                    off += p
-                dist.all_gather_into_tensor(st["gathered"].view(-1), st["mine"], group=self.group)
-                rebuild_from_gathered(st["gathered"], st["per"], [self.full[i] for i in st["idx"]])
+                gather_stage(self.hosts, st["idx"], st["per"], st["mine"], st["gathered"], self.full, self.rank, self.group)
                 st["event"].record(self.side)
         main.wait_event(self.stages[0]["event"])
         maps, vols, T = self.full[:self.n_maps], self.full[self.n_maps:-1], self.full[-1]

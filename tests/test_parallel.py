@@ -82,3 +82,52 @@ def test_sliced_upload_reassembles_every_tensor():
         parallel.rebuild_from_gathered(gathered, per, fulls)
         for a, b in zip(fulls, tensors):
             assert torch.equal(a, b)
+
+
+def _stage_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)                      # same tensors on every rank
+        maps = [torch.rand(1, 4, 6, 6, generator=g), torch.rand(1, 8, 3, 3, generator=g)]
+        vols = [torch.rand(1, 1, 32, 32, 32, generator=g), torch.rand(1, 3, 20, 20, 20, generator=g),
+                torch.rand(1, 8, 16, 16, 16, generator=g), torch.rand(1, 8, 5, 5, 5, generator=g)]
+        T = torch.rand(1, 4, 3, generator=g)
+        hosts = [*maps, *vols, T]
+        stages, late = parallel.upload_stages([v.shape[2] for v in vols], len(maps), len(hosts))
+        fulls = [torch.full_like(t, float("nan")) for t in hosts]
+        per_all = [-(-t.numel() // world) for t in hosts]
+        seen = []
+        for idx in stages:
+            per = [per_all[i] for i in idx]
+            mine = torch.zeros(sum(per))
+            gathered = torch.empty(world, sum(per))
+            parallel.gather_stage(hosts, idx, per, mine, gathered, fulls, rank)
+            seen.append([bool(torch.equal(fulls[i], hosts[i])) for i in range(len(hosts))])
+        q.put((rank, stages, late, seen))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_staged_upload_gloo_world2():
+    """The two-stage upload of the multi-rank end-to-end path: after stage 1 exactly the coarse tensors (maps, levels
+    with R <= 16, T) are complete on every rank, after stage 2 all of them."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_stage_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, stages, late, seen in res:
+        assert late == [0, 1] and stages == [[0, 1, 4, 5, 6], [2, 3]], (stages, late)
+        assert seen[0] == [True, True, False, False, True, True, True], seen
+        assert seen[1] == [True] * 7, seen
+
+
+def test_upload_stages_without_fine_levels_is_one_stage():
+    stages, late = parallel.upload_stages([16, 8, 4], 2, 6)
+    assert late == [] and stages == [[0, 1, 2, 3, 4, 5]]
