@@ -64,3 +64,14 @@ def test_cpu_tensors_are_rejected_loudly():
         hotpath.prepare_context([torch.zeros(1, 8, 4, 4)], [torch.zeros(1, 8, 2, 2, 2)], torch.zeros(1, 4, 3))
     with pytest.raises(RuntimeError):
         hotpath.grid_points(4, device="cpu")
+
+
+def test_staged_and_host_entry_points_reject_bad_arguments_without_a_gpu():
+    """Argument validation of the host-buffer / staged dense-grid calls happens before any CUDA work."""
+    lib = _C.lib()
+    rc = lib.list_sdf_grid_late(None, None, 8, -0.5, 0.5, 0, 8, None, 1.0, 8, None, 0, None, None, None, None)
+    assert rc == _C.EINVAL and "ctx is NULL" in _C.last_error()
+    rc = lib.list_sdf_grid_host(None, None, None, 5, 137, None, 6, None, None, None, 1, _C.BF16, None, 8, -0.5, 0.5, 0, 8,
+                                1.0, 8, None, None, 0, None)
+    assert rc == _C.EINVAL and "NULL argument" in _C.last_error()
+    assert lib.list_sdf_grid_host_bytes(None, None, 5, 137, 6, None, None, 1, _C.BF16, 8, 8) == 0
