@@ -150,3 +150,38 @@ def test_port_and_restatement_vs_live_reference():
         rest = O.list_query(inp.maps, inp.vols, inp.trans_mat, inp.points, inp.weights)
     assert (port - ref).abs().max() <= 2e-6
     assert (rest - ref).abs().max() <= FP32_TOL / 4
+
+
+def test_projection_commutes_with_the_samplers():
+    """The algebra behind the hoisted fc_0 of the dense-grid path (csrc/hoist.cu), checked on the
+    oracle alone: fc_0 is linear and so are the bilinear (zeros padding) and trilinear (border padding) samplers, so
+    projecting a feature tensor through its block of W0 and sampling the 512-wide result equals sampling first and
+    multiplying after -- including taps that fall outside the map, NaN grids, clamped voxel coordinates and the seven
+    displaced copies; and the unshifted trilinear weights sum to one, which is what lets a constant (the bias) ride
+    along in a projected volume."""
+    g = torch.Generator().manual_seed(5)
+    B, N, S, C, R, Cv, n0 = 2, 257, 9, 16, 5, 8, 12
+    maps_cl = torch.randn(B, S, S, C, generator=g, dtype=torch.float64)
+    vol_cl = torch.randn(B, R, R, R, Cv, generator=g, dtype=torch.float64)
+    Wm = torch.randn(n0, C, generator=g, dtype=torch.float64)
+    Wv = torch.randn(7, n0, Cv, generator=g, dtype=torch.float64)                 # one W0 block per displacement
+    xy = (torch.rand(B, N, 2, generator=g, dtype=torch.float64) * 1.4 - 0.2) * (S - 1)   # some taps out of bounds
+    xy[0, 0] = float("nan")
+    xy[0, 1] = torch.tensor([S - 1.0, S - 1.0])
+    q = torch.rand(B, N, 3, generator=g, dtype=torch.float64) * 2.6 - 1.3        # beyond the border on all sides
+    # a-3: sample then project == project then sample
+    a = O.gather2d(maps_cl, xy) @ Wm.t()
+    b = O.gather2d(maps_cl @ Wm.t(), xy)
+    assert torch.allclose(a, b, rtol=0, atol=1e-12)
+    # a-5: per displacement d, its own W0 block
+    disp = O.displacements(torch.float64)
+    lhs = sum(O.gather3d(vol_cl, q + disp[d]) @ Wv[d].t() for d in range(7))
+    rhs = sum(O.gather3d(vol_cl @ Wv[d].t(), q + disp[d]) for d in range(7))
+    assert torch.allclose(lhs, rhs, rtol=0, atol=1e-11)
+    # a constant rides along exactly once per sample: trilinear weights sum to one under border padding
+    ones = torch.ones(B, R, R, R, 1, dtype=torch.float64)
+    assert torch.allclose(O.gather3d(ones, q), torch.ones(B, N, 1, dtype=torch.float64), rtol=0, atol=1e-13)
+    # ... but not the bilinear weights with zeros padding (why the bias is not folded into the projected map)
+    ones2 = torch.ones(B, S, S, 1, dtype=torch.float64)
+    w = O.gather2d(ones2, xy)
+    assert (w < 1 - 1e-6).any() and torch.all(w <= 1 + 1e-12)
