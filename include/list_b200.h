@@ -37,7 +37,7 @@ extern "C" {
 #define LIST_API
 #endif
 
-#define LIST_B200_ABI_VERSION 1
+#define LIST_B200_ABI_VERSION 2
 #define LIST_MAX_LEVELS 8
 #define LIST_MAX_MAPS 8
 #define LIST_NUM_DISP 7          /* reference network/modules.py:205-212 */
@@ -196,6 +196,32 @@ LIST_API int list_mlp_hoisted_fwd(const ListWeights* w, int32_t hoist_cols, cons
 LIST_API int list_mlp_hoisted_trace(const ListWeights* w, int32_t hoist_cols, const void* Xh, int64_t ldx, int64_t rows,
                            float* sdf, float out_div, int64_t* trace, void* stream);
 
+/* Line-table path for dense grids in bf16 mode (csrc/lines.cu + csrc/grid_tc.cu), the default of list_sdf_grid.
+ * As above the maps and the coarse voxel levels (here R <= 32) are projected through their column blocks of W0 once per
+ * image, but the 512-wide addend block is never materialised: along a z-line of the grid (reference utils.py:84-95) the
+ * trilinear sample of a projected level is a two-tap interpolation in ONE column table per (level, W-shift class)
+ * (list_lines_table), and the MLP kernel evaluates those interpolations and the bilinear taps of the projected map as
+ * a small extra GEMM on the tensor cores, accumulating into fc_0's TMEM tile (list_grid_tc_fwd; reference
+ * modules.py:48-53, 262-282).  list_sdf_grid runs the stages internally; they are exposed for tests and timing.
+ *   list_lines_layout      hoist_cols, k_f = k_pad - hoist_cols (columns of the dense part Xr), rows per line table
+ *   list_lines_hoist_bytes size of the caller-owned buffer with the projected tensors (0: configuration not covered)
+ *   list_lines_prepare     projects every image of ctx into hoist_buf
+ *   list_lines_table       G[lines touched by [begin, begin+count)][rows_per_line][512] bf16 of `image`
+ *   list_lines_rest        Xr[count][ldx >= k_f]: the non-hoisted feature columns (fine levels, q, zero pad)
+ *   list_grid_tc_fwd       sdf[count] = MLP(Xr, interpolated hoisted terms) / out_div.  dbg_h1 (or NULL): relu(fc_0) as
+ *                          fp32 [count][512]; trace (or NULL): phase timeline as in list_mlp_hoisted_trace */
+LIST_API int list_lines_layout(const ListCtx* ctx, const ListWeights* w, int32_t* hoist_cols, int32_t* k_f, int32_t* rows_per_line);
+LIST_API size_t list_lines_hoist_bytes(const ListCtx* ctx, const ListWeights* w);
+LIST_API int list_lines_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, void* stream);
+LIST_API size_t list_lines_table_bytes(const ListCtx* ctx, const ListWeights* w, int32_t res, int64_t begin, int64_t count);
+LIST_API int list_lines_table(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
+                     double bb_min, double bb_max, int64_t begin, int64_t count, void* G, size_t G_bytes, void* stream);
+LIST_API int list_lines_rest(const ListCtx* ctx, const ListWeights* w, int32_t image, int32_t res, double bb_min, double bb_max,
+                    int64_t begin, int64_t count, void* Xr, int64_t ldx, void* stream);
+LIST_API int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
+                     double bb_min, double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G,
+                     float* sdf, float out_div, float* dbg_h1, int64_t* trace, void* stream);
+
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
  * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */
 LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min,
@@ -205,10 +231,10 @@ LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res
 /* Staged variant for callers that are still producing the fine volumes (upload, all-gather ...) on another
  * stream: every level l with late_vols_ncdhw[l] != NULL is NOT yet valid in ctx->vols[l]; the call waits for
  * late_event (a cudaEvent_t recorded after the producer's last write, or NULL) right before its first kernel
- * that reads such a level -- the projection and the first chunk's addend gather run before that -- and prepares
+ * that reads such a level -- the projection and the first chunk's line tables run before that -- and prepares
  * the level itself (list_prep_volume from the reference-layout fp32 DEVICE tensor late_vols_ncdhw[l] into
  * ctx->vols[l]).  sdf_host (pinned host memory, [B][count], or NULL) additionally receives every chunk's values
- * behind the next chunk's kernels.  Levels with R <= 16 and C % 64 == 0 may be read by the projection and cannot
+ * behind the next chunk's kernels.  Levels with R <= 32 and C % 64 == 0 may be read by the projection and cannot
  * be late (LIST_EINVAL).  late_vols_ncdhw == NULL and sdf_host == NULL: same as list_sdf_grid. */
 LIST_API int list_sdf_grid_late(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min,
                        double bb_max, int64_t begin, int64_t count, float* sdf, float sdf_scale,

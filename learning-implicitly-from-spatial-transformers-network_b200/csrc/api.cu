@@ -45,8 +45,6 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
                float* dbg1, float* dbg2, float* dbg3, cudaStream_t st);
 int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
                        float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, long long* trace, cudaStream_t st);
-int sdf_grid_fused(const ListCtx* ctx, const ListWeights* w, int image, int res, double bb_min, double bb_max,
-                   int64_t begin, int64_t count, float* sdf, float out_div, cudaStream_t st);
 
 static size_t elem_size(int dtype) { return dtype == LIST_BF16 ? 2 : 4; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -92,13 +90,6 @@ static int grid_gather(const ListCtx* ctx, int image, int res, double bb_min, do
     if (rc != LIST_ENOSYS) return rc;
   }
   return gather_grid_fwd(ctx, image, res, bb_min, bb_max, begin, count, X, ldx, st);
-}
-
-// The fused kernel is used when it is the faster path (LIST_B200_FUSED=1/0 overrides).
-static bool fused_default() {
-  const char* e = getenv("LIST_B200_FUSED");
-  if (e) return e[0] == '1';
-  return false;
 }
 
 static int mlp_variant() {
@@ -160,13 +151,21 @@ static bool hoist_enabled() {
   return !(e && e[0] == '0');
 }
 
+// Line-table path (lines.cu + grid_tc.cu): the hoisted terms are interpolated on the tensor cores inside the MLP kernel.
+// Default for bf16 dense grids; LIST_B200_LINES=0 selects the round-1 addend-kernel path (A/B aid).
+static bool lines_enabled() {
+  static const bool on = []() { const char* e = getenv("LIST_B200_LINES"); return !(e && e[0] == '0'); }();
+  return on;
+}
+constexpr int kLinesLevels = 3, kLinesMaxRes = 32;     // hoisted levels of the line-table path
+
 static bool overlap_enabled() {
   const char* e = getenv("LIST_B200_OVERLAP");
   return !(e && e[0] == '0');
 }
 
 // Hooks of the host-buffer entry point into the dense-grid evaluation.  Upload, evaluation and download overlap:
-//   * the coarse per-image tensors (maps, levels with R <= 16, T) are uploaded and prepared first; the projection and
+//   * the coarse per-image tensors (maps, levels with R <= 32, T) are uploaded and prepared first; the projection and
 //     the addend part of the first chunk's gather only need those, so they run while the big volumes are still on the
 //     wire.  `late` (wait for the upload, prepare the remaining levels) runs on the gather stream right before the
 //     first kernel that reads them;
@@ -390,6 +389,8 @@ size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_
   size_t extra = 0;
   hoist::Plan pl;
   if (ctx->dtype == LIST_BF16 && hoist::make_plan(ctx, w, &pl) == LIST_OK) extra = align_up(pl.total, 256);
+  if (ctx->dtype == LIST_BF16 && hoist::make_plan(ctx, w, &pl, kLinesLevels, kLinesMaxRes) == LIST_OK && align_up(pl.total, 256) > extra)
+    extra = align_up(pl.total, 256);
   return (ctx->dtype == LIST_BF16 ? 2 * xb : xb) + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256) + extra;
 }
 
@@ -452,6 +453,103 @@ int list_mlp_hoisted_trace(const ListWeights* w, int32_t hoist_cols, const void*
   LIST_CHECK_ARG(hoist_cols > 0 && hoist_cols < w->k_pad && hoist_cols % 64 == 0, "list_mlp_hoisted_trace: hoist_cols %d invalid", hoist_cols);
   return mlp_tc_fwd_hoisted(w, hoist_cols, w->k_pad - hoist_cols, Xh, ldx, rows, sdf, out_div, mlp_variant(), nullptr, nullptr, nullptr,
                             reinterpret_cast<long long*>(trace), static_cast<cudaStream_t>(stream));
+}
+
+// ---- line-table path, stage by stage (tests, per-kernel timing) ----
+static int lines_plan(const ListCtx* ctx, const ListWeights* w, hoist::Plan* pl, const char* who) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  if ((rc = check_weights(w, -1))) return rc;
+  if (hoist::make_plan(ctx, w, pl, kLinesLevels, kLinesMaxRes) != LIST_OK) {
+    set_error("%s: this configuration has no hoisted path (bf16, fc_0 width 512, coarse levels with C %% 64 == 0)", who);
+    return LIST_ENOSYS;
+  }
+  return LIST_OK;
+}
+static int check_range(int32_t res, int64_t begin, int64_t count, const char* who) {
+  LIST_CHECK_ARG(res >= 1 && res <= 2048, "%s: res %d out of range", who, res);
+  const int64_t total = static_cast<int64_t>(res) * res * res;
+  LIST_CHECK_ARG(begin >= 0 && count >= 0 && begin + count <= total, "%s: [%lld,+%lld) outside res^3", who, (long long)begin, (long long)count);
+  return LIST_OK;
+}
+
+size_t list_lines_hoist_bytes(const ListCtx* ctx, const ListWeights* w) {
+  hoist::Plan pl;
+  if (!ctx || !w || lines_plan(ctx, w, &pl, "list_lines_hoist_bytes")) return 0;
+  return pl.total;
+}
+
+int list_lines_layout(const ListCtx* ctx, const ListWeights* w, int32_t* hoist_cols, int32_t* k_f, int32_t* rows_per_line) {
+  hoist::Plan pl;
+  const int rc = lines_plan(ctx, w, &pl, "list_lines_layout");
+  if (rc) return rc;
+  if (hoist_cols) *hoist_cols = pl.hoist_cols;
+  if (k_f) *k_f = pl.k_h - 512;
+  if (rows_per_line) *rows_per_line = pl.rpl;
+  return LIST_OK;
+}
+
+int list_lines_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, void* stream) {
+  hoist::Plan pl;
+  const int rc = lines_plan(ctx, w, &pl, "list_lines_prepare");
+  if (rc) return rc;
+  if (!hoist_buf || hoist_bytes < pl.total || (reinterpret_cast<uintptr_t>(hoist_buf) & 255)) {
+    set_error("list_lines_prepare: hoist_buf NULL, not 256B aligned or %zu B < required %zu B", hoist_bytes, pl.total);
+    return LIST_ENOMEM;
+  }
+  return hoist::prepare(ctx, w, pl, hoist_buf, static_cast<cudaStream_t>(stream));
+}
+
+size_t list_lines_table_bytes(const ListCtx* ctx, const ListWeights* w, int32_t res, int64_t begin, int64_t count) {
+  hoist::Plan pl;
+  if (!ctx || !w || res < 1 || lines_plan(ctx, w, &pl, "list_lines_table_bytes")) return 0;
+  return hoist::lines_bytes(pl, res, begin, count);
+}
+
+int list_lines_table(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res, double bb_min,
+                     double bb_max, int64_t begin, int64_t count, void* G, size_t G_bytes, void* stream) {
+  hoist::Plan pl;
+  int rc = lines_plan(ctx, w, &pl, "list_lines_table");
+  if (rc) return rc;
+  if ((rc = check_range(res, begin, count, "list_lines_table"))) return rc;
+  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_lines_table: image %d outside [0,%d)", image, ctx->B);
+  LIST_CHECK_ARG(hoist_buf && G && (reinterpret_cast<uintptr_t>(G) & 15) == 0, "list_lines_table: hoist_buf / G NULL or G unaligned");
+  if (G_bytes < hoist::lines_bytes(pl, res, begin, count)) {
+    set_error("list_lines_table: G %zu B < required %zu B", G_bytes, hoist::lines_bytes(pl, res, begin, count));
+    return LIST_ENOMEM;
+  }
+  return hoist::lines(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, G, static_cast<cudaStream_t>(stream));
+}
+
+int list_lines_rest(const ListCtx* ctx, const ListWeights* w, int32_t image, int32_t res, double bb_min, double bb_max, int64_t begin,
+                    int64_t count, void* Xr, int64_t ldx, void* stream) {
+  hoist::Plan pl;
+  int rc = lines_plan(ctx, w, &pl, "list_lines_rest");
+  if (rc) return rc;
+  if ((rc = check_range(res, begin, count, "list_lines_rest"))) return rc;
+  if (hoist::check_gather(ctx, pl, res) != LIST_OK) {
+    set_error("list_lines_rest: res %d not covered by the rest kernel", res);
+    return LIST_ENOSYS;
+  }
+  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_lines_rest: image %d outside [0,%d)", image, ctx->B);
+  LIST_CHECK_ARG(Xr && ldx >= pl.k_h - 512 && ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(Xr) & 15) == 0,
+                 "list_lines_rest: Xr NULL / unaligned or ldx %lld < %d", (long long)ldx, pl.k_h - 512);
+  // the rest kernel addresses columns relative to a row that starts with the 512 addend columns of the round-1 layout
+  return hoist::gather(ctx, w, pl, nullptr, image, res, bb_min, bb_max, begin, count, static_cast<__nv_bfloat16*>(Xr) - 512, ldx,
+                       hoist::kPartRest, static_cast<cudaStream_t>(stream));
+}
+
+int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res, double bb_min,
+                     double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G, float* sdf, float out_div,
+                     float* dbg_h1, int64_t* trace, void* stream) {
+  hoist::Plan pl;
+  int rc = lines_plan(ctx, w, &pl, "list_grid_tc_fwd");
+  if (rc) return rc;
+  if ((rc = check_range(res, begin, count, "list_grid_tc_fwd"))) return rc;
+  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_grid_tc_fwd: image %d outside [0,%d)", image, ctx->B);
+  LIST_CHECK_ARG(hoist_buf && Xr && G && sdf && out_div != 0.f, "list_grid_tc_fwd: NULL argument or out_div == 0");
+  return grid_tc_fwd(ctx, w, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, Xr, ldx, G, sdf, out_div, dbg_h1,
+                     reinterpret_cast<long long*>(trace), static_cast<cudaStream_t>(stream));
 }
 
 int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
@@ -549,23 +647,7 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
   if (count == 0) return LIST_OK;
   LIST_CHECK_ARG(sdf != nullptr && sdf_scale != 0.f && chunk_rows >= 1, "list_sdf_grid: sdf NULL, sdf_scale 0 or chunk_rows < 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // bf16: ONE fused gather->MLP launch per image (sdf_fused.cu), no feature rows in HBM, no workspace.
-  // LIST_B200_NO_FUSED=1 (A/B aid) or an uncovered configuration -> chunked gather + MLP kernels.
-  const char* nf = getenv("LIST_B200_NO_FUSED");
-  bool fused = ctx->dtype == LIST_BF16 && !(nf && nf[0] == '1') && fused_default();
-  int b0 = 0;
   bool late_done = false;
-  if (fused) {
-    if ((rc = hook_late(hooks, st))) return rc;
-    late_done = true;
-    for (; b0 < ctx->B; ++b0) {
-      rc = sdf_grid_fused(ctx, w, b0, res, bb_min, bb_max, begin, count, sdf + static_cast<int64_t>(b0) * count, sdf_scale, st);
-      if (rc == LIST_ENOSYS && b0 == 0) { fused = false; break; }
-      if (rc) return rc;
-      if ((rc = hook_download(hooks, sdf, static_cast<int64_t>(b0) * count, count, st))) return rc;
-    }
-    if (fused) return LIST_OK;
-  }
   const size_t need = list_sdf_workspace_bytes(ctx, w, chunk_rows);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("list_sdf_grid: workspace %zu B < required %zu B", workspace_bytes, need);
@@ -582,7 +664,40 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
     n0 = (i % per_image) * chunk_rows;
     n = (count - n0 < chunk_rows) ? (count - n0) : chunk_rows;
   };
-  // bf16: hoisted fc_0 (hoist.cu) -- project maps / coarse levels through their W0 blocks once per call, then the
+  // bf16, line-table path (default): project the maps and the coarse levels (R <= 32) through their W0 blocks once per
+  // call (hoist::prepare); per chunk, lines.cu reduces the projected levels to one column table per z-line, the rest
+  // kernel writes the non-hoisted feature columns, and grid_tc.cu interpolates the hoisted terms on the tensor cores inside
+  // the MLP kernel.  A chunk's buffer holds [Xr: rows x k_f | G: line tables].
+  hoist::Plan pl3;
+  if (two && hoist_enabled() && lines_enabled() && hoist::make_plan(ctx, w, &pl3, kLinesLevels, kLinesMaxRes) == LIST_OK &&
+      hoist::check_gather(ctx, pl3, res) == LIST_OK) {
+    const int k_f = pl3.k_h - 512;
+    const size_t xr_bytes = align_up(static_cast<size_t>(chunk_rows) * k_f * 2, 256);
+    if (xr_bytes + hoist::lines_bytes(pl3, res, res - 1, chunk_rows) <= xb) {
+      void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+      if ((rc = hoist::prepare(ctx, w, pl3, hbuf, st))) return rc;
+      return run_chunks(
+          per_image * ctx->B, xbuf, overlap_enabled(), st,
+          [&](int64_t i, void* X, cudaStream_t s) -> int {
+            int b; int64_t n0, n;
+            span(i, b, n0, n);
+            int r2 = hoist::lines(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, static_cast<char*>(X) + xr_bytes, s);
+            if (r2) return r2;
+            // the line tables only read the projected tensors; everything uploaded late is first read by the rest kernel
+            if (i == 0 && !late_done && hooks && hooks->late && (r2 = hook_late(hooks, s))) return r2;
+            return hoist::gather(ctx, w, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, static_cast<__nv_bfloat16*>(X) - 512, k_f,
+                                 hoist::kPartRest, s);
+          },
+          [&](int64_t i, void* X, cudaStream_t s) -> int {
+            int b; int64_t n0, n;
+            span(i, b, n0, n);
+            const int r2 = grid_tc_fwd(ctx, w, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, k_f, static_cast<char*>(X) + xr_bytes,
+                                       sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, nullptr, nullptr, s);
+            return r2 ? r2 : hook_download(hooks, sdf, static_cast<int64_t>(b) * count + n0, n, s);
+          });
+    }
+  }
+  // bf16, addend-kernel path (round 1; LIST_B200_LINES=0 or a configuration the line-table path does not cover): the
   // per-chunk gather writes the hoisted row [addend 512 | 832 columns]; fc_0 runs on the 832 columns and adds the addend
   // block in its epilogue.
   hoist::Plan pl;
@@ -649,10 +764,10 @@ int list_sdf_grid_late(const ListCtx* ctx, const ListWeights* w, int32_t res, do
   if (late_vols_ncdhw) {
     LIST_CHECK_ARG(w != nullptr && ctx->n_levels >= 1 && ctx->n_levels <= LIST_MAX_LEVELS, "list_sdf_grid_late: bad ctx / weights");
     hoist::Plan pl;                                     // the projection runs first and reads the hoisted levels
-    if (ctx->dtype == LIST_BF16 && hoist_enabled() && hoist::make_plan(ctx, w, &pl) == LIST_OK)
+    if (ctx->dtype == LIST_BF16 && hoist_enabled() && hoist::make_plan(ctx, w, &pl, kLinesLevels, kLinesMaxRes) == LIST_OK)
       for (int h = 0; h < pl.nh; ++h)
         LIST_CHECK_ARG(late_vols_ncdhw[pl.lev[h]] == nullptr,
-                       "list_sdf_grid_late: level %d (R <= 16, C %% 64 == 0) is read by the projection and cannot be late", pl.lev[h]);
+                       "list_sdf_grid_late: level %d (R <= 32, C %% 64 == 0) is read by the projection and cannot be late", pl.lev[h]);
     hooks.uploaded = static_cast<cudaEvent_t>(late_event);
     hooks.user = &late;
     hooks.late = [](void* u, cudaStream_t s) -> int {
@@ -702,10 +817,10 @@ static void plan_host(const int32_t* map_ch, const int32_t* map_in, int n_maps, 
   size_t ws = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(dtype), 256);
   if (dtype == LIST_BF16) {
     ws *= 2;                                           // double-buffered feature rows (run_chunks)
-    // hoisted-fc_0 tensors (hoist.cu): projected maps + 7 projected copies of every level with R <= 16
-    size_t h = align_up(static_cast<size_t>(B) * S * S * 512 * 2, 256);
+    // hoisted-fc_0 tensors (hoist.cu): projected maps + 7 projected copies of every level with R <= 32
+    size_t h = align_up(static_cast<size_t>(B) * S * S * 512 * 2, 256) + 1024;
     for (int l = 0; l < n_levels; ++l)
-      if (vol_res[l] <= 16) h += align_up(static_cast<size_t>(7) * B * vol_res[l] * vol_res[l] * vol_res[l] * 512 * 2, 256);
+      if (vol_res[l] <= kLinesMaxRes) h += align_up(static_cast<size_t>(7) * B * vol_res[l] * vol_res[l] * vol_res[l] * 512 * 2, 256);
     ws += h + 256;
   }
   if (dtype == LIST_F32) ws += align_up(static_cast<size_t>(chunk_rows) * (512 + 256 + 256) * 4, 256);
@@ -747,7 +862,7 @@ int list_sdf_grid_host(const float* const* maps_host, const int32_t* map_ch, con
   Pipe* pp = nullptr;
   int rc;
   if ((rc = get_pipe(&pp))) return rc;
-  // Uploads run on the copy stream, ordered after the caller's stream: T, maps and the coarse levels (R <= 16: all the
+  // Uploads run on the copy stream, ordered after the caller's stream: T, maps and the coarse levels (R <= 32: all the
   // projection and the addend gather read) first, then the other levels from coarse to fine.
   LIST_CUDA(cudaEventRecord(pp->cfork, st));
   LIST_CUDA(cudaStreamWaitEvent(pp->cp, pp->cfork, 0));
@@ -766,11 +881,11 @@ int list_sdf_grid_host(const float* const* maps_host, const int32_t* map_ch, con
   for (int i = 1; i < n_levels; ++i)                                      // insertion sort: coarse levels first, then by size
     for (int j = i; j > 0; --j) {
       const int x = order[j - 1], y = order[j];
-      const bool sx = vol_res[x] <= 16, sy = vol_res[y] <= 16;
+      const bool sx = vol_res[x] <= kLinesMaxRes, sy = vol_res[y] <= kLinesMaxRes;
       if ((sy && !sx) || (sx == sy && vol_bytes(y) < vol_bytes(x))) { order[j - 1] = y; order[j] = x; } else break;
     }
   int n_small = 0;
-  while (n_small < n_levels && vol_res[order[n_small]] <= 16) ++n_small;
+  while (n_small < n_levels && vol_res[order[n_small]] <= kLinesMaxRes) ++n_small;
   for (int i = 0; i < n_small; ++i)
     LIST_CUDA(cudaMemcpyAsync(base + p.raw_vols[order[i]], vols_host[order[i]], vol_bytes(order[i]), cudaMemcpyHostToDevice, pp->cp));
   LIST_CUDA(cudaEventRecord(pp->small, pp->cp));

@@ -1,0 +1,797 @@
+// Dense-grid SDF evaluation, bf16 tensor-core mode: interpolation of the hoisted fc_0 terms AND the implicit MLP in ONE
+// persistent warp-specialised sm_100a kernel (rows a-3, a-5, a-6, a-8 of SURVEY.md §8; reference network/modules.py:48-53,
+// 262-282 inside the chunk loop of network/executors.py:215-224).
+//
+// fc_0 is linear and so are the samplers in front of it, so the contribution of the perceptual maps and of the coarse
+// voxel levels to fc_0's pre-activation is  sample(W0[:, cols] . tensor, p)  (hoist.cu projects the tensors once per image,
+// lines.cu reduces the projected levels to one column table per z-line).  What is left per query is a SPARSE linear
+// combination of 512-wide bf16 rows: 4 bilinear taps of the projected map P and, per hoisted level and W-shift class, the
+// two neighbours of the line's column table G.  A tile of 128 consecutive steps of a z-line touches only ~120 distinct
+// rows, so the combination is evaluated on the tensor cores, accumulating into the same TMEM tile as fc_0's dense part:
+//
+//     acc[128 x 512]  =  Xr[128 x K_F] . W0[:, hoisted..]^T            (F chunks: TMA operands, as in mlp_tc.cu)
+//                      +  Aw[128 x rows] . Brows[rows x 512]           (I chunks: Aw = interpolation weights written by the
+//                                                                       interp warps, Brows = rows of P / G copied with
+//                                                                       cp.async; MN-major B operand)
+// followed by bias + ReLU, fc_1, fc_2, fc_out exactly as mlp_tc.cu (activations stay in TMEM).  The 512-wide "addend"
+// block of round 1 (34 GB through HBM per 256^3 grid) no longer exists.
+//
+//   Warp roles : warp 0 = TMA producer and ring allocator, warp 1 = TMEM allocator + MMA issuer (one thread),
+//                warps 2..5 = epilogue (one TMEM lane quarter each), warps 6..9 = interp warps (tile plan, Aw, Brows).
+//   CG = 2     : CTA pair, tcgen05.mma.cta_group::2, M = 256.  CTA r evaluates tile 2p + r; the K space of the pair's
+//                I chunks is the concatenation of both tiles' row lists (the other CTA's rows get zero weights), and each
+//                CTA copies ITS half of the 512 channels of every listed row (B operand split along N).
+//   Ring       : 12 units of 16 KB, allocated first-in first-out by the TMA thread in consumption order
+//                  F chunk [X box | W0 box | W0 box] -> I chunk [Aw | Brows j=0 | Brows j=1] -> 8 + 4 weight boxes of fc_1 / fc_2.
+//                I chunks are filled by the interp warps once the allocator has granted their units (grant barriers).
+//   Row lists  : built per tile by the interp warps ("plan"): voxel rows = contiguous node ranges of the line table per
+//                (level, class); pixel rows = the nodes of the pixel cells the tile's path crosses, de-duplicated between
+//                consecutive cells (a node shared with the previous cell keeps its slot).  Both CTAs of a pair build
+//                both plans (deterministic), so they agree on the chunk count without communicating.
+#include <cstdlib>
+
+#include "grid_common.cuh"
+#include "hoist.cuh"
+#include "tc_common.cuh"
+
+namespace list {
+namespace gtc {
+
+using namespace tc;
+using hoist::TileMap;
+using hoist::TileSpan;
+
+constexpr int CG = 2;
+constexpr int BM = 128, BK = 64;
+constexpr int N0 = 512, N1 = 256, N2 = 256;
+constexpr int UNIT_BYTES = 128 * BK * 2;           // 16 KB
+constexpr int NU = 12, NB = 12;                    // ring units / chunk barriers
+constexpr int U_FI = 3;                            // units of an F or I chunk
+constexpr int N_W = (N0 + N1) / BK;                // fc_1 + fc_2 weight chunks per tile, one unit each
+constexpr int kEpiWarp0 = 2, kIntWarp0 = 6, kIntWarps = 4;
+constexpr int kThreads = (kIntWarp0 + kIntWarps) * 32;   // 320
+constexpr int kMaxLev = hoist::kMaxLev;
+constexpr int NC = kMaxLev * 3;                    // (level, W-shift class) combinations
+constexpr int kEnt = 2 * NC + 4;                   // weight entries of a step: two per combination + 4 pixel taps
+constexpr int kMaxRows = 832;                      // rows of one tile's list: <= 3 * sum R voxel + 4 * 128 pixel, 64-aligned
+constexpr uint32_t kEmpty = 0xffff0000u;           // weight entry that matches no chunk
+constexpr uint32_t kKindG = 0u, kKindPix = 1u << 30, kKindZero = 2u << 30, kIdxMask = (1u << 30) - 1;
+
+// ---- shared-memory carve-up (offsets from the 1024-byte aligned base) ----
+constexpr int OFF_PAR = NU * UNIT_BYTES;                           // b0 b1 b2 w3 (fp32)
+constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;
+constexpr int OFF_ENT = OFF_PAR + PARAM_FLOATS * 4;                // uint32 [128][kEnt]: slot << 16 | bf16 weight
+constexpr int OFF_ROWS = OFF_ENT + BM * kEnt * 4;                  // uint32 [2][kMaxRows]: kind | row index
+constexpr int OFF_KEY = OFF_ROWS + 2 * kMaxRows * 4;               // int [128] pixel cell of a step (-1: none)
+constexpr int OFF_CKEY = OFF_KEY + BM * 4;                         // int [128] cell -> key
+constexpr int OFF_CBASE = OFF_CKEY + BM * 4;                       // int [128] cell -> first new slot
+constexpr int OFF_CMASK = OFF_CBASE + BM * 4;                      // int [128] cell -> new mask | valid mask << 4
+constexpr int OFF_CSLOT = OFF_CMASK + BM * 4;                      // short [128][4] cell -> slot of its 4 nodes
+constexpr int OFF_MISC = OFF_CSLOT + BM * 4 * 2;                   // int first[NC] last[NC] scan[8] plan[2][2]
+constexpr int MISC_INTS = 2 * NC + 8 + 4 + 2;
+constexpr int OFF_BAR = (OFF_MISC + MISC_INTS * 4 + 7) / 8 * 8;
+constexpr int NUM_BARS = 3 * NB + 2 + 2;                           // full empty grant | dfull hready | plan[2]
+constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024 /*align slack*/;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+struct Params {
+  const float *b0, *b1, *b2, *w3, *b3;
+  float* sdf;                       // [count] of this image
+  float out_div;
+  int nkF;                          // F chunks: (k_pad - hoist_cols) / 64
+  int x_rows;                       // rows of the X map (= count)
+  TileMap tm;
+  unsigned n_tiles;
+  const __nv_bfloat16* pmap;        // projected map of the image [S*S][512]
+  const __nv_bfloat16* G;           // line tables [lines][rpl][512]
+  const __nv_bfloat16* zero;        // 512 zeros
+  const float* T;
+  int S, nh, rpl;
+  int R[kMaxLev], rowbase[kMaxLev];
+  float* dbg1;                      // optional [count][512]: relu(fc_0) in fp32 before rounding
+  long long* trace;
+  uint32_t b_lbo, b_sbo, b_kadv;    // MN-major descriptor of the Brows units: bytes between 64-channel groups / 8-row groups / 16 k rows
+};
+
+__device__ __forceinline__ void tile_rows(const TileMap& m, unsigned tile, unsigned n_tiles, int64_t& g0, int& s_lo, int& s_hi) {
+  if (tile >= n_tiles) { g0 = m.end; s_lo = 0; s_hi = 0; return; }
+  const unsigned lrel = tile / static_cast<unsigned>(m.segs);
+  const unsigned seg = tile - lrel * static_cast<unsigned>(m.segs);
+  const int gz0 = static_cast<int>(seg) << m.lg_kpz;
+  g0 = (m.line0 + lrel) * m.res + gz0;
+  const int full = min(m.kPz, m.res - gz0);
+  s_lo = static_cast<int>(max(static_cast<int64_t>(0), m.begin - g0));
+  s_hi = static_cast<int>(min(static_cast<int64_t>(full), m.end - g0));
+  if (s_hi < s_lo) s_hi = s_lo;
+}
+
+// UMMA shared-memory descriptor of an MN-major operand, 128B swizzle (cute: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
+// units): a k row is 64 elements = 128 B, 8 k rows form a 1024 B swizzle atom, SBO = bytes between 8-row groups along K,
+// LBO = bytes between 64-element groups along N.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory");
+}
+// acquire at cluster scope: the barrier was (also) arrived on by the peer CTA, whose shared memory the MMA will read
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  if (mbar_try_cluster(bar, parity)) return;
+  long long t0 = 0;
+  uint32_t polls = 0;
+  while (!mbar_try_cluster(bar, parity)) {
+    if ((++polls & 63u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) mbar_timeout(bar, parity);
+    }
+  }
+}
+__device__ __forceinline__ uint32_t bf16_bits(float x) { return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(x))); }
+
+// ------------------------------------------------------------------ tile plan (interp warps, 128 threads, thread = step)
+struct PlanSmem {
+  uint32_t* ent;      // [128][kEnt]
+  uint32_t* rows;     // [2][kMaxRows]
+  int* key;           // [128]
+  int* ckey;          // [128]
+  int* cbase;         // [128]
+  int* cmask;         // [128]
+  short* cslot;       // [128][4]
+  int* first;         // [NC]
+  int* last;          // [NC]
+  int* scan;          // [8]
+};
+
+__device__ __forceinline__ void ibar() { named_bar_sync(2, kIntWarps * 32); }
+
+// Builds list L (rows of tile `tile`) and, if `own`, the weight entries of this CTA's 128 steps.  Returns the number of
+// 64-row chunks of the list.  All 128 interp threads call it with the same arguments.
+__device__ __noinline__ int plan_list(const Params& p, const PlanSmem& sm, unsigned tile, int L, bool own, int it) {
+  TileSpan t;
+  const bool live = tile < p.n_tiles && tile_span(p.tm, tile, t);
+  if (!live) {
+    if (own) {
+#pragma unroll
+      for (int e = 0; e < kEnt; ++e) sm.ent[it * kEnt + e] = kEmpty;
+    }
+    return 0;
+  }
+  const int lane = it & 31, w = it >> 5;
+  const int s = it;
+  const bool valid = s >= t.s_lo && s < t.s_hi;
+  const int S = p.S;
+  const float q0 = valid ? step_q0(p.tm, t, s) : 0.f;
+  // ---- pixel cell and bilinear weights (reference modules.py:37-52) ----
+  int key = -1, x0 = 0, y0 = 0;
+  float pw[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    const float q[3] = {q0, t.qy, t.qz};
+    float ix, iy, h[3];
+    localise(q, p.T, S, ix, iy, h);
+    if (ix == ix && iy == iy) {                                   // NaN grid -> all taps out of bounds
+      const float fx = floorf(ix), fy = floorf(iy);
+      x0 = static_cast<int>(fx); y0 = static_cast<int>(fy);
+      const float wx1 = ix - fx, wx0 = (fx + 1.0f) - ix;
+      const float wy1 = iy - fy, wy0 = (fy + 1.0f) - iy;
+      pw[0] = wx0 * wy0; pw[1] = wx1 * wy0; pw[2] = wx0 * wy1; pw[3] = wx1 * wy1;
+      key = y0 * S + x0;
+    }
+  }
+  sm.key[s] = key;
+  // ---- voxel index / weights per (level, class) ----
+  int vi0[NC];
+  uint32_t vw[NC];                                                // bf16 w0 | bf16 w1 << 16, i1 == i0 flagged by w1 == 0xffff
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    vi0[c] = 0; vw[c] = 0;
+    if (c / 3 < p.nh) {
+      const int R = p.R[c / 3];
+      const Axis3 ax = axis_border(q0 + hoist::class_shift(c % 3), R);
+      vi0[c] = ax.i0;
+      // the larger weight is rounded to bf16, the smaller one is its exact complement (representable): the pair sums to 1
+      const bool big0 = ax.w0 >= ax.w1;
+      const float a = __bfloat162float(__float2bfloat16_rn(big0 ? ax.w0 : ax.w1));
+      const float b = 1.0f - a;
+      const uint32_t w0b = bf16_bits(big0 ? a : b), w1b = bf16_bits(big0 ? b : a);
+      vw[c] = w0b | ((ax.i1 != ax.i0 ? w1b : 0xffffu) << 16);
+      if (s == t.s_lo) sm.first[c] = ax.i0;
+      if (s == t.s_hi - 1) sm.last[c] = ax.i1;
+    }
+  }
+  ibar();
+  int vbase[NC + 1];
+  vbase[0] = 0;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) vbase[c + 1] = vbase[c] + (c / 3 < p.nh ? sm.last[c] - sm.first[c] + 1 : 0);
+  const int nvox = vbase[NC];
+  // ---- pixel cells: a step opens a new cell when its key differs from the previous step's ----
+  const bool isnew = key >= 0 && (s == 0 || sm.key[s - 1] != key);
+  const uint32_t bal = __ballot_sync(0xffffffffu, isnew);
+  if (lane == 0) sm.scan[w] = __popc(bal);
+  ibar();
+  int woff = 0;
+#pragma unroll
+  for (int i = 0; i < kIntWarps; ++i) woff += i < w ? sm.scan[i] : 0;
+  const int mycell = woff + __popc(bal & ((1u << lane) - 1u)) + (isnew ? 1 : 0) - 1;   // cell of this step (-1: none yet)
+  if (isnew) sm.ckey[mycell] = key;
+  ibar();
+  // ---- which nodes of a new cell are new (not shared with the previous cell) ----
+  int newmask = 0, validmask = 0;
+  if (isnew) {
+    const int pk = mycell > 0 ? sm.ckey[mycell - 1] : -1;
+    const int py0 = pk >= 0 ? pk / S : 0, px0 = pk >= 0 ? pk - py0 * S : 0;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int nx = x0 + (n & 1), ny = y0 + (n >> 1);
+      const bool v = nx <= S - 1 && ny <= S - 1;
+      const bool sh = pk >= 0 && static_cast<unsigned>(nx - px0) <= 1u && static_cast<unsigned>(ny - py0) <= 1u;
+      if (v) validmask |= 1 << n;
+      if (v && !sh) newmask |= 1 << n;
+    }
+  }
+  const int cnt = __popc(newmask);
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) sm.scan[4 + w] = inc;
+  ibar();
+  int wbase = 0, npix = 0;
+#pragma unroll
+  for (int i = 0; i < kIntWarps; ++i) { wbase += i < w ? sm.scan[4 + i] : 0; npix += sm.scan[4 + i]; }
+  const int base = wbase + inc - cnt;
+  if (isnew) { sm.cbase[mycell] = base; sm.cmask[mycell] = newmask | (validmask << 4); }
+  ibar();
+  uint32_t* const rows = sm.rows + L * kMaxRows;
+  if (isnew) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      int slot = -1;
+      if ((validmask >> n) & 1) {
+        const int nx = x0 + (n & 1), ny = y0 + (n >> 1);
+        if ((newmask >> n) & 1) {
+          slot = base + __popc(newmask & ((1 << n) - 1));
+          rows[nvox + slot] = kKindPix | static_cast<uint32_t>(ny * S + nx);
+        } else {
+          for (int cc = mycell - 1; cc >= 0; --cc) {              // the node keeps the slot of the cell that introduced it
+            const int ck = sm.ckey[cc];
+            const int cy0 = ck / S, cx0 = ck - cy0 * S;
+            const int which = (nx - cx0) + 2 * (ny - cy0);
+            const int m = sm.cmask[cc];
+            if ((m >> which) & 1) { slot = sm.cbase[cc] + __popc(m & ((1 << which) - 1)); break; }
+          }
+        }
+      }
+      sm.cslot[mycell * 4 + n] = static_cast<short>(slot);
+    }
+  }
+  // ---- voxel rows: contiguous node ranges of the line table ----
+  const uint32_t line_row0 = t.line_rel * static_cast<uint32_t>(p.rpl);
+  for (int e = it; e < nvox; e += kIntWarps * 32) {
+    int c = 0;
+#pragma unroll
+    for (int i = 1; i < NC; ++i)
+      if (e >= vbase[i]) c = i;
+    rows[e] = kKindG | (line_row0 + static_cast<uint32_t>(p.rowbase[c / 3] + (c % 3) * p.R[c / 3] + sm.first[c] + (e - vbase[c])));
+  }
+  const int n_rows = nvox + npix;
+  const int n_chunks = (n_rows + BK - 1) / BK;
+  for (int e = n_rows + it; e < n_chunks * BK; e += kIntWarps * 32) rows[e] = kKindZero;
+  ibar();
+  if (own) {
+    uint32_t* const ent = sm.ent + s * kEnt;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      uint32_t e0 = kEmpty, e1 = kEmpty;
+      if (c / 3 < p.nh && valid) {
+        const uint32_t slot0 = static_cast<uint32_t>(vbase[c] + vi0[c] - sm.first[c]);
+        e0 = (slot0 << 16) | (vw[c] & 0xffffu);
+        if ((vw[c] >> 16) != 0xffffu) e1 = ((slot0 + 1) << 16) | (vw[c] >> 16);
+      }
+      ent[2 * c] = e0;
+      ent[2 * c + 1] = e1;
+    }
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      uint32_t e = kEmpty;
+      if (key >= 0) {
+        const int cs = sm.cslot[mycell * 4 + n];
+        if (cs >= 0) e = (static_cast<uint32_t>(nvox + cs) << 16) | bf16_bits(pw[n]);
+      }
+      ent[2 * NC + n] = e;
+    }
+  }
+  return n_chunks;
+}
+
+// ------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(kThreads, 1)
+grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
+               const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* const gbase = smem_raw + (base - raw);
+  float* const s_par = reinterpret_cast<float*>(gbase + OFF_PAR);
+  float* const s_b0 = s_par;
+  float* const s_b1 = s_b0 + N0;
+  float* const s_b2 = s_b1 + N1;
+  float* const s_w3 = s_b2 + N2;
+  int* const s_misc = reinterpret_cast<int*>(gbase + OFF_MISC);
+  volatile int* const s_plan = s_misc + 2 * NC + 8;              // [2][2] chunk counts of the two lists, double buffered
+  const uint32_t bar0 = base + OFF_BAR;
+  auto full_bar = [&](uint32_t b) { return bar0 + 8u * b; };
+  auto empty_bar = [&](uint32_t b) { return bar0 + 8u * (NB + b); };
+  auto grant_bar = [&](uint32_t b) { return bar0 + 8u * (2 * NB + b); };
+  const uint32_t dfull_bar = bar0 + 8u * (3 * NB);
+  const uint32_t hready_bar = dfull_bar + 8u;
+  auto plan_bar = [&](uint32_t i) { return hready_bar + 8u + 8u * i; };
+  const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
+  volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + NUM_BARS * 8);
+  auto unit_addr = [&](uint32_t u) { return base + (u % NU) * UNIT_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x / CG;
+  const int num_clusters = gridDim.x / CG;
+  const int n_pairs = static_cast<int>((p.n_tiles + 1) / 2);
+  const int nkF = p.nkF;
+
+  constexpr int kTraceTiles = 16, kTraceSlots = 12;
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+  auto stamp = [&](int tile_no, int slot) {
+    if (tracing && tile_no < kTraceTiles) p.trace[tile_no * kTraceSlots + slot] = clock64();
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmW0);
+    tma_prefetch_desc(&tmW1);
+    tma_prefetch_desc(&tmW2);
+    for (int b = 0; b < NB; ++b) {
+      mbar_init(full_bar(b), CG);                     // one arrival per CTA (TMA thread or an interp warp)
+      mbar_init(empty_bar(b), 1);
+      mbar_init(grant_bar(b), 1);
+    }
+    mbar_init(dfull_bar, 1);
+    mbar_init(hready_bar, 4 * CG);
+    mbar_init(plan_bar(0), 1);
+    mbar_init(plan_bar(1), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc<CG>(tmem_slot);
+  if (warp >= kEpiWarp0 && warp < kIntWarp0) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < PARAM_FLOATS; i += 128) {
+      float v;
+      if (i < N0) v = __ldg(p.b0 + i);
+      else if (i < N0 + N1) v = __ldg(p.b1 + i - N0);
+      else if (i < N0 + N1 + N2) v = __ldg(p.b2 + i - N0 - N1);
+      else v = __ldg(p.w3 + i - N0 - N1 - N2);
+      s_par[i] = v;
+    }
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // =========================== TMA producer / ring allocator ===========================
+    if (lane == 0) {
+      uint32_t q = 0, head = 0, tail_q = 0;
+      int free_units = NU;
+      unsigned long long fifo = 0;                    // unit counts of the chunks in flight, oldest in bit 0 (1 = 3 units)
+      int fifo_n = 0;
+      auto make_room = [&](int n) {
+        while (free_units < n) {
+          mbar_wait(empty_bar(tail_q % NB), (tail_q / NB) & 1);
+          free_units += (fifo & 1ull) ? U_FI : 1;
+          fifo >>= 1;
+          --fifo_n;
+          ++tail_q;
+        }
+        free_units -= n;
+        fifo |= static_cast<unsigned long long>(n == U_FI ? 1 : 0) << fifo_n;
+        ++fifo_n;
+      };
+      // one arrival per CTA on the leader's full barrier; the leader's also announces the bytes of BOTH CTAs
+      auto announce = [&](uint32_t b, uint32_t bytes_per_cta) {
+        if (rank == 0) mbar_expect_tx(full_bar(b), CG * bytes_per_cta);
+        else mbar_arrive_cluster(mapa(full_bar(b), 0));
+      };
+      int itn = 0;
+      for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+        int64_t g0;
+        int s_lo, s_hi;
+        tile_rows(p.tm, 2u * pair + rank, p.n_tiles, g0, s_lo, s_hi);
+        const int row0 = static_cast<int>(g0 - p.tm.begin);   // may be negative / past the end: TMA zero-fills those rows
+        for (int kc = 0; kc < nkF; ++kc, ++q, head += U_FI) {
+          make_room(U_FI);
+          const uint32_t b = q % NB;
+          const uint32_t fb = mapa(full_bar(b), 0);
+          announce(b, U_FI * UNIT_BYTES);
+          tma_load_2d<CG>(&tmX, fb, unit_addr(head), kc * BK, row0);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d<CG>(&tmW0, fb, unit_addr(head + 1 + j), kc * BK, j * 256 + static_cast<int>(rank) * 128);
+        }
+        mbar_wait(plan_bar(itn & 1), (itn >> 1) & 1);
+        const int nI = s_plan[(itn & 1) * 2] + s_plan[(itn & 1) * 2 + 1];
+        for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {      // units for the interp warps
+          make_room(U_FI);
+          mbar_arrive_local(grant_bar(q % NB));
+        }
+#pragma unroll 1
+        for (int layer = 1; layer <= 2; ++layer) {
+          const CUtensorMap* tm = (layer == 1) ? &tmW1 : &tmW2;
+          const int nk = (layer == 1 ? N0 : N1) / BK;
+          for (int kc = 0; kc < nk; ++kc, ++q, ++head) {
+            make_room(1);
+            const uint32_t b = q % NB;
+            announce(b, UNIT_BYTES);
+            tma_load_2d<CG>(tm, mapa(full_bar(b), 0), unit_addr(head), kc * BK, static_cast<int>(rank) * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (leader CTA, one thread) ===========================
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc(128 * CG, 128 * CG);
+      constexpr uint32_t idesc_mn = idesc | (1u << 16);           // B operand MN-major (rows of P / G are N-contiguous)
+      constexpr uint32_t kCols = 128 * CG;
+      uint32_t q = 0, head = 0, hphase = 0, fphase = 0;
+      auto wait_full = [&]() {
+        const uint32_t b = q % NB;
+        mbar_wait_cluster(full_bar(b), (fphase >> b) & 1u);
+        fphase ^= 1u << b;
+        tc_fence_after();
+      };
+      int itn = 0;
+      for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+        if (itn > 0) { mbar_wait(hready_bar, hphase); hphase ^= 1; }   // previous tile's accumulators drained
+        tc_fence_after();
+        stamp(itn, 0);
+        // ---- fc_0, dense part: D[0,512) = Xr . W0[:, hoisted..]^T ----
+        for (int kc = 0; kc < nkF; ++kc, head += U_FI) {
+          wait_full();
+          const uint64_t ad = umma_desc_sw128(unit_addr(head));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k, umma_desc_sw128(unit_addr(head + 1 + j)) + 2 * k, idesc,
+                          (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<CG>(empty_bar(q % NB));
+          ++q;
+        }
+        // ---- fc_0, interpolated part: D += Aw . Brows ----
+        mbar_wait(plan_bar(itn & 1), (itn >> 1) & 1);
+        const int nI = s_plan[(itn & 1) * 2] + s_plan[(itn & 1) * 2 + 1];
+        for (int ci = 0; ci < nI; ++ci, head += U_FI) {
+          wait_full();
+          const uint64_t ad = umma_desc_sw128(unit_addr(head));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)     // 16 k rows = 2048 B further along K
+              umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k,
+                          umma_desc_mn_sw128(unit_addr(head + 1 + j), p.b_lbo, p.b_sbo) + static_cast<uint64_t>((p.b_kadv >> 4) * k),
+                          idesc_mn, 1u);
+          }
+          umma_commit<CG>(empty_bar(q % NB));
+          ++q;
+        }
+        umma_commit<CG>(dfull_bar);
+        stamp(itn, 1);
+        // ---- fc_1: D[256,512) = H1(TMEM [0,256)) . W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) . W2^T ----
+#pragma unroll 1
+        for (int layer = 1; layer <= 2; ++layer) {
+          const int nk = (layer == 1 ? N0 : N1) / BK;
+          mbar_wait(hready_bar, hphase); hphase ^= 1;
+          tc_fence_after();
+          stamp(itn, 2 * layer);
+          for (int kc = 0; kc < nk; ++kc, ++head) {
+            wait_full();
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_ts<CG>(tmem_base + 256, tmem_base + kc * (BK / 2) + k * 8, umma_desc_sw128(unit_addr(head)) + 2 * k, idesc,
+                          (kc | k) != 0 ? 1u : 0u);
+            umma_commit<CG>(empty_bar(q % NB));
+            ++q;
+          }
+          umma_commit<CG>(dfull_bar);
+          stamp(itn, 2 * layer + 1);
+        }
+      }
+    }
+  } else if (warp < kIntWarp0) {
+    // =========================== epilogue warps ===========================
+    const int quarter = warp & 3;
+    const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    const uint32_t hready_remote = mapa(hready_bar, 0);
+    const float bias3 = __ldg(p.b3);
+    const int r_in_tile = quarter * 32 + lane;
+    auto arrive_hready = [&]() {
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(hready_remote);
+    };
+    uint32_t dphase = 0;
+    int itn = 0;
+    const bool estamp = warp == kEpiWarp0 && lane == 0;
+    for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+      int64_t g0;
+      int s_lo, s_hi;
+      tile_rows(p.tm, 2u * pair + rank, p.n_tiles, g0, s_lo, s_hi);
+      const bool live = r_in_tile >= s_lo && r_in_tile < s_hi;
+      const int64_t orow = g0 + r_in_tile - p.tm.begin;
+      // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
+      mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
+      tc_fence_after();
+      if (estamp) stamp(itn, 6);
+#pragma unroll 1
+      for (int j = 0; j < N0 / 32; ++j) {
+        uint32_t v[32], u[16];
+        tmem_ld32(tq + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_b0 + j * 32 + 2 * i);
+          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+          u[i] = pack_bf16x2_relu(sum.x, sum.y);
+        }
+        tmem_st16(tq + j * 16, u);
+        if (p.dbg1 != nullptr && live) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) p.dbg1[orow * N0 + j * 32 + i] = fmaxf(__uint_as_float(v[i]) + s_b0[j * 32 + i], 0.f);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      if (estamp) stamp(itn, 7);
+      arrive_hready();
+      // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) ----
+      mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
+      tc_fence_after();
+      if (estamp) stamp(itn, 8);
+#pragma unroll 1
+      for (int j = 0; j < N1 / 32; ++j) {
+        uint32_t v[32], u[16];
+        tmem_ld32(tq + 256 + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_b1 + j * 32 + 2 * i);
+          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+          u[i] = pack_bf16x2_relu(sum.x, sum.y);
+        }
+        tmem_st16(tq + j * 16, u);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      if (estamp) stamp(itn, 9);
+      arrive_hready();
+      // ---- after fc_2: sdf = (relu(acc + b2) . w3 + b3) / out_div ----
+      mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
+      tc_fence_after();
+      if (estamp) stamp(itn, 10);
+      float2 acc2 = make_float2(0.f, 0.f);
+#pragma unroll 1
+      for (int j = 0; j < N2 / 32; ++j) {
+        uint32_t v[32];
+        tmem_ld32(tq + 256 + j * 32, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float2 bb = *reinterpret_cast<const float2*>(s_b2 + j * 32 + 2 * i);
+          const float2 ww = *reinterpret_cast<const float2*>(s_w3 + j * 32 + 2 * i);
+          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+          acc2 = ffma2(make_float2(fmaxf(sum.x, 0.f), fmaxf(sum.y, 0.f)), ww, acc2);
+        }
+      }
+      tc_fence_before();
+      if (estamp) stamp(itn, 11);
+      arrive_hready();
+      if (live) p.sdf[orow] = __fdiv_rn((acc2.x + acc2.y) + bias3, p.out_div);
+    }
+  } else {
+    // =========================== interp warps ===========================
+    const int it = threadIdx.x - kIntWarp0 * 32;                   // 0..127 = step of the tile
+    const int wq = it >> 5;
+    PlanSmem sm;
+    sm.ent = reinterpret_cast<uint32_t*>(gbase + OFF_ENT);
+    sm.rows = reinterpret_cast<uint32_t*>(gbase + OFF_ROWS);
+    sm.key = reinterpret_cast<int*>(gbase + OFF_KEY);
+    sm.ckey = reinterpret_cast<int*>(gbase + OFF_CKEY);
+    sm.cbase = reinterpret_cast<int*>(gbase + OFF_CBASE);
+    sm.cmask = reinterpret_cast<int*>(gbase + OFF_CMASK);
+    sm.cslot = reinterpret_cast<short*>(gbase + OFF_CSLOT);
+    sm.first = s_misc;
+    sm.last = s_misc + NC;
+    sm.scan = s_misc + 2 * NC;
+    const uint32_t ent_addr = base + OFF_ENT;
+    // this lane's part of a listed row: j = which 256-channel block of N0, g = which 64-channel group of the CTA's 128, c16 = 16-byte piece
+    const int bj = lane >> 4, bg = (lane >> 3) & 1, bc = lane & 7;
+    const int col_off = bj * 256 + static_cast<int>(rank) * 128 + bg * 64 + bc * 8;
+    uint32_t q = 0, head = 0, gphase = 0;
+    int itn = 0;
+    for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+      ibar();                                                      // every warp is done with the previous tile's lists
+      const int nI0 = plan_list(p, sm, 2u * pair, 0, rank == 0, it);
+      const int nI1 = plan_list(p, sm, 2u * pair + 1, 1, rank == 1, it);
+      if (it == 0) { s_plan[(itn & 1) * 2] = nI0; s_plan[(itn & 1) * 2 + 1] = nI1; }
+      ibar();
+      if (it == 0) mbar_arrive_local(plan_bar(itn & 1));
+      const int nI = nI0 + nI1;
+      q += nkF;
+      head += U_FI * nkF;
+      for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {
+        const uint32_t b = q % NB;
+        const uint32_t par = (gphase >> b) & 1u;
+        gphase ^= 1u << b;
+        if ((ci & (kIntWarps - 1)) != wq) continue;                // chunk ci belongs to warp ci % 4
+        const int L = ci >= nI0 ? 1 : 0;
+        const int c = L ? ci - nI0 : ci;
+        mbar_wait_warp(grant_bar(b), par);
+        // ---- Aw: zeros, then this CTA's weights if the list is its own tile's ----
+        const uint32_t ua = unit_addr(head);
+#pragma unroll 8
+        for (int i = 0; i < UNIT_BYTES / 16 / 32; ++i) st_shared_zero16(ua + static_cast<uint32_t>(i * 32 + lane) * 16u);
+        __syncwarp();
+        if (L == static_cast<int>(rank)) {
+#pragma unroll 1
+          for (int rr = 0; rr < BM / 32; ++rr) {
+            const int row = rr * 32 + lane;
+            const uint32_t ra = ua + static_cast<uint32_t>(row) * 128u;
+#pragma unroll
+            for (int e = 0; e < kEnt; ++e) {
+              uint32_t v;
+              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ent_addr + static_cast<uint32_t>(row * kEnt + e) * 4u) : "memory");
+              if (static_cast<int>(v >> 22) == c) {
+                const uint32_t col = (v >> 16) & 63u;
+                st_shared_u16(ra + ((((col >> 3) ^ static_cast<uint32_t>(row & 7))) << 4) + (col & 7u) * 2u, v & 0xffffu);
+              }
+            }
+          }
+        }
+        // ---- Brows: this CTA's 256 channels of the 64 listed rows, MN-major 128B-swizzled (row k of a 64-channel group
+        //      at (k / 8) * 1024 + (k % 8) * 128, 16-byte piece i at (i ^ (k % 8)) * 16; groups 8 KB apart) ----
+        const uint32_t ub = unit_addr(head + 1 + bj) + static_cast<uint32_t>(bg) * 8192u;
+        const uint32_t* const lrows = sm.rows + L * kMaxRows + c * BK;
+#pragma unroll 8
+        for (int k = 0; k < BK; ++k) {
+          const uint32_t r = lrows[k];
+          const uint32_t kind = r & ~kIdxMask;
+          const __nv_bfloat16* src = kind == kKindG ? p.G : (kind == kKindPix ? p.pmap : p.zero);
+          src += static_cast<size_t>(kind == kKindZero ? 0u : (r & kIdxMask)) * N0 + col_off;
+          cp_async16(ub + static_cast<uint32_t>(k >> 3) * 1024u + static_cast<uint32_t>(k & 7) * 128u +
+                         (static_cast<uint32_t>(bc ^ (k & 7)) << 4), src);
+        }
+        cp_async_wait_all();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive_local(full_bar(b));
+          else mbar_arrive_cluster(mapa(full_bar(b), 0));
+        }
+      }
+      q += N_W;
+      head = (head + N_W) % NU;
+    }
+  }
+
+  // =========================== teardown ===========================
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<CG>(tmem_base);
+  }
+}
+
+}  // namespace gtc
+
+// Fused interpolation + MLP over grid points [begin, begin + count) of image `image` (see the header comment).
+int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, const void* hoist_buf, int image, int res,
+                double bb_min, double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G, float* sdf,
+                float out_div, float* dbg1, long long* trace, cudaStream_t st) {
+  using namespace gtc;
+  if (count == 0) return LIST_OK;
+  LIST_CHECK_ARG(w->n0 == N0 && w->n1 == N1 && w->n2 == N2, "grid_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
+  LIST_CHECK_ARG(count < (1LL << 31), "grid_tc: %lld rows are too many for one launch", (long long)count);
+  const int k_f = pl.k_h - N0;
+  LIST_CHECK_ARG(k_f >= BK && k_f % BK == 0 && ldx >= k_f && ldx % 8 == 0, "grid_tc: %d dense columns / ldx %lld invalid", k_f, (long long)ldx);
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(Xr) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, "grid_tc: Xr / G must be 16-byte aligned");
+  LIST_CHECK_ARG(pl.nh <= kMaxLev && ctx->map_size * ctx->map_size < (1 << 30), "grid_tc: plan not covered");
+  for (int h = 0; h < pl.nh; ++h)
+    LIST_CHECK_ARG(ctx->vol_res[pl.lev[h]] <= 32, "grid_tc: hoisted level with R = %d > 32", ctx->vol_res[pl.lev[h]]);
+  Params p{};
+  p.b0 = w->b0; p.b1 = w->b1; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.sdf = sdf;
+  p.out_div = out_div;
+  p.nkF = k_f / BK;
+  p.x_rows = static_cast<int>(count);
+  hoist::fill_tilemap(&p.tm, res, bb_min, bb_max, begin, count, BM);
+  p.n_tiles = hoist::tile_count(p.tm);
+  LIST_CHECK_ARG(static_cast<uint64_t>(hoist::line_count(p.tm)) * pl.rpl < (1ull << 30), "grid_tc: line table too large for one launch");
+  const char* hb = static_cast<const char*>(hoist_buf);
+  p.pmap = reinterpret_cast<const __nv_bfloat16*>(hb + pl.off_pmap) + static_cast<size_t>(image) * ctx->map_size * ctx->map_size * N0;
+  p.G = static_cast<const __nv_bfloat16*>(G);
+  p.zero = reinterpret_cast<const __nv_bfloat16*>(hb + pl.off_zero);
+  p.T = ctx->trans_mat + image * 12;
+  p.S = ctx->map_size;
+  p.nh = pl.nh;
+  p.rpl = pl.rpl;
+  for (int h = 0; h < kMaxLev; ++h) {
+    p.R[h] = h < pl.nh ? ctx->vol_res[pl.lev[h]] : 1;
+    p.rowbase[h] = h < pl.nh ? pl.rowbase[h] : 0;
+  }
+  p.dbg1 = dbg1;
+  p.trace = trace;
+  p.b_lbo = 8192; p.b_sbo = 1024; p.b_kadv = 2048;
+  if (const char* e = getenv("LIST_B200_TC_DESC")) {           // bring-up aid: "lbo,sbo,kadv" in bytes
+    unsigned a = 0, b = 0, c = 0;
+    if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { p.b_lbo = a; p.b_sbo = b; p.b_kadv = c; }
+  }
+  int vox_rows = 0;
+  for (int h = 0; h < pl.nh; ++h) vox_rows += 3 * ctx->vol_res[pl.lev[h]];
+  LIST_CHECK_ARG(vox_rows + 4 * BM <= kMaxRows, "grid_tc: %d voxel rows per tile exceed the row list", vox_rows);
+  CUtensorMap tmX, tmW0, tmW1, tmW2;
+  int rc;
+  if ((rc = make_map_bf16(&tmX, Xr, static_cast<uint64_t>(k_f), static_cast<uint64_t>(count), static_cast<uint64_t>(ldx)))) return rc;
+  if ((rc = make_map_bf16(&tmW0, static_cast<const __nv_bfloat16*>(w->w0) + pl.hoist_cols, static_cast<uint64_t>(k_f), N0, w->k_pad))) return rc;
+  if ((rc = make_map_bf16(&tmW1, w->w1, N0, N1, N0))) return rc;
+  if ((rc = make_map_bf16(&tmW2, w->w2, N1, N2, N1))) return rc;
+  int dev = 0, sms = 0;
+  LIST_CUDA(cudaGetDevice(&dev));
+  LIST_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  static thread_local int attr_dev = -1;
+  if (attr_dev != dev) {
+    LIST_CUDA(cudaFuncSetAttribute(grid_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_dev = dev;
+  }
+  const int n_pairs = static_cast<int>((p.n_tiles + 1) / 2);
+  const int clusters = n_pairs < sms / CG ? n_pairs : sms / CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CG);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LIST_CUDA(cudaLaunchKernelEx(&cfg, grid_tc_kernel, tmX, tmW0, tmW1, tmW2, p));
+  return LIST_OK;
+}
+
+}  // namespace list

@@ -29,6 +29,7 @@
 //                        to gather_grid.cu's, in two divergence-free phases through a shared-memory column table.
 #include <cstdlib>
 
+#include "grid_common.cuh"
 #include "hoist.cuh"
 
 namespace list {
@@ -37,45 +38,6 @@ int mlp_tc_project(const ListWeights* w, int col0, int col_stride, int groups, i
                    int64_t rows, void* out, cudaStream_t st);
 
 namespace hoist {
-
-// Tiles never straddle z-runs: tile t = (z-line, segment of kPz steps of that line), clipped to the launch's
-// point range [begin, end).  Everything a tile computes is therefore a function of absolute grid positions
-// only, which is what makes any chunking / sharding of the grid bit-identical.
-struct TileMap {
-  int64_t line0;                    // first z-line (flat index / res) touched by [begin, end); < res^2 <= 2^22
-  int64_t begin, end;               // flat grid range of this launch
-  int segs;                         // tiles per z-line
-  int kPz, lg_kpz;                  // steps per tile (a power of two)
-  int res;
-  double bb_min, bb_max, step;      // step = (bb_max - bb_min) / (res - 1), the linspace increment
-};
-
-struct TileSpan {
-  int64_t g_tile0;                  // flat grid index of step 0
-  int gz0;                          // its position on the z-line
-  int s_lo, s_hi;                   // steps of the tile inside [begin, end)
-  float qy, qz;                     // swapped/scaled query components 1 (-> H) and 2 (-> D), constant over the tile
-};
-
-// 32-bit index arithmetic only (64-bit divisions cost ~100 instructions each and every thread of a tile runs this)
-__device__ __forceinline__ bool tile_span(const TileMap& m, unsigned tile, TileSpan& t) {
-  const unsigned lrel = tile / static_cast<unsigned>(m.segs);
-  const unsigned seg = tile - lrel * static_cast<unsigned>(m.segs);
-  const unsigned line = static_cast<unsigned>(m.line0) + lrel;
-  const unsigned lz = line / static_cast<unsigned>(m.res), ly = line - lz * static_cast<unsigned>(m.res);
-  t.gz0 = static_cast<int>(seg) << m.lg_kpz;
-  t.g_tile0 = static_cast<int64_t>(line) * m.res + t.gz0;
-  const int full = min(m.kPz, m.res - t.gz0);
-  t.s_lo = static_cast<int>(max(static_cast<int64_t>(0), m.begin - t.g_tile0));
-  t.s_hi = static_cast<int>(min(static_cast<int64_t>(full), m.end - t.g_tile0));
-  // reference utils.py:84-95 (x slowest, z fastest) and models.py:91-92 ([2,1,0] swap, *2)
-  t.qy = linspace_f32_step(static_cast<int>(ly), m.res, m.bb_min, m.bb_max, m.step) * 2.0f;
-  t.qz = linspace_f32_step(static_cast<int>(lz), m.res, m.bb_min, m.bb_max, m.step) * 2.0f;
-  return t.s_lo < t.s_hi;
-}
-__device__ __forceinline__ float step_q0(const TileMap& m, const TileSpan& t, int s) {
-  return linspace_f32_step(t.gz0 + s, m.res, m.bb_min, m.bb_max, m.step) * 2.0f;
-}
 
 constexpr int kTile = 128;          // max steps per tile (rest kernel)
 #ifndef LIST_ADD_TILE
@@ -88,8 +50,6 @@ constexpr int kRestThreads = 256;
 constexpr int kRestLevels = 4;      // non-hoisted levels (vector ones first)
 constexpr int kMaxVec = 128;        // 16-byte items of the non-hoisted vector levels
 constexpr int kMaxTail = 64;        // tail columns: scalar levels, q, zero pad
-
-struct Corner { uint32_t base; float w; };
 
 struct AddParams {
   const __nv_bfloat16* pmap;        // image's [S][S][512]
@@ -123,27 +83,9 @@ struct RestParams {
   TileMap tm;
 };
 
-__device__ __forceinline__ int shift_class(int d) { return d == 1 ? 1 : (d == 2 ? 2 : 0); }
 __device__ __forceinline__ int warp_of(int tid) { return tid >> 5; }
-__device__ __forceinline__ float class_shift(int cls) { return cls == 0 ? 0.f : (cls == 1 ? -kDisplacement : kDisplacement); }
 // floor(a / b) for 0 <= a < 2^20, 1 <= b < 2^10 through the float reciprocal (exact in that range)
 __device__ __forceinline__ int fast_div(int a, float inv_b) { return static_cast<int>((static_cast<float>(a) + 0.5f) * inv_b); }
-
-// (H, D) corners and weights of displacement d for a tile (same arithmetic as gather_grid.cu)
-__device__ __forceinline__ void tile_corners(float qy, float qz, int d, int R, uint32_t row_elems, uint32_t base[4], float wyz[4]) {
-  const float q[3] = {0.f, qy, qz};
-  float pd[3];
-  displaced(q, d, pd);
-  const Axis3 ay = axis_border(pd[1], R), az = axis_border(pd[2], R);
-  const int zi[2] = {az.i0, az.i1}, yi[2] = {ay.i0, ay.i1};
-  const float wz[2] = {az.w0, az.w1}, wy[2] = {ay.w0, ay.w1};
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int tz = k >> 1, ty = k & 1;
-    base[k] = (static_cast<uint32_t>(zi[tz]) * R + yi[ty]) * R * row_elems;
-    wyz[k] = wy[ty] * wz[tz];
-  }
-}
 
 // ------------------------------------------------------------------ addend
 // V consecutive bf16 channels (V = 8: 16-byte, V = 4: 8-byte accesses)
@@ -600,18 +542,22 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
 // ------------------------------------------------------------------ host side
 // Which part of the row is hoisted: the maps and the leading vector levels of the layout (coarsest first)
 // whose projected volumes stay small (R <= 16) and whose channel count feeds the tensor-core projection (C % 64).
-int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl) {
+int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl, int max_levels, int max_res) {
   if (ctx->dtype != LIST_BF16 || w->dtype != LIST_BF16 || w->n0 != kN0) return LIST_ENOSYS;
   if (ctx->map_channels % 64 != 0) return LIST_ENOSYS;
+  if (max_levels > kMaxLev) max_levels = kMaxLev;
   ListLayout lay;
   const int rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr);
   if (rc) return rc;
   if (lay.map_off != 0 || w->k_pad != lay.k_pad) return LIST_ENOSYS;
   pl->nh = 0;
+  pl->rpl = 0;
   int cols = ctx->map_channels;
-  for (int l = ctx->n_levels - 1; l >= 0 && pl->nh < kMaxH; --l) {       // layout order of the vector levels
+  for (int l = ctx->n_levels - 1; l >= 0 && pl->nh < max_levels; --l) {       // layout order of the vector levels
     if (ctx->vol_ch[l] % 8) continue;
-    if (ctx->vol_res[l] > 16 || ctx->vol_ch[l] % 64 != 0 || lay.vol_off[l] != cols) break;
+    if (ctx->vol_res[l] > max_res || ctx->vol_ch[l] % 64 != 0 || lay.vol_off[l] != cols) break;
+    pl->rowbase[pl->nh] = pl->rpl;
+    pl->rpl += 3 * ctx->vol_res[l];
     pl->lev[pl->nh++] = l;
     cols += LIST_NUM_DISP * ctx->vol_ch[l];
   }
@@ -627,6 +573,7 @@ int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl) {
     pl->off_pvol[h] = off;
     off += up(static_cast<size_t>(LIST_NUM_DISP) * ctx->B * R * R * R * kN0 * 2);
   }
+  pl->off_zero = off; off += up(kN0 * 2);                                  // one all-zero row (padding rows of grid_tc.cu)
   pl->total = off;
   return LIST_OK;
 }
@@ -648,6 +595,7 @@ int prepare(const ListCtx* ctx, const ListWeights* w, const Plan& pl, void* buf,
                              base + pl.off_pvol[h], st)))
       return rc;
   }
+  LIST_CUDA(cudaMemsetAsync(base + pl.off_zero, 0, kN0 * 2, st));
   return LIST_OK;
 }
 
@@ -749,24 +697,6 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
   return LIST_ENOSYS;
 }
 
-static void fill_tilemap(TileMap* tm, int res, double bb_min, double bb_max, int64_t begin, int64_t count, int kpz) {
-  tm->line0 = begin / res;
-  tm->begin = begin;
-  tm->end = begin + count;
-  tm->kPz = kpz;
-  tm->lg_kpz = 0;
-  while ((1 << tm->lg_kpz) < kpz) ++tm->lg_kpz;
-  tm->segs = (res + kpz - 1) / kpz;
-  tm->res = res;
-  tm->bb_min = bb_min;
-  tm->bb_max = bb_max;
-  tm->step = res > 1 ? (bb_max - bb_min) / static_cast<double>(res - 1) : 0.0;
-}
-static unsigned tile_count(const TileMap& tm) {
-  const int64_t lines = (tm.end - 1) / tm.res - tm.line0 + 1;
-  return static_cast<unsigned>(lines * tm.segs);
-}
-
 // LIST_OK if gather() covers a res^3 grid of this configuration.
 int check_gather(const ListCtx* ctx, const Plan& pl, int res) {
   ListLayout lay;
@@ -787,14 +717,18 @@ int gather(const ListCtx* ctx, const ListWeights* w, const Plan& pl, const void*
   const char* base = static_cast<const char*>(buf);
   AddParams a{};
   a.pmap = reinterpret_cast<const __nv_bfloat16*>(base + pl.off_pmap) + static_cast<size_t>(image) * ctx->map_size * ctx->map_size * kN0;
-  a.nh = pl.nh;
-  for (int h = 0; h < pl.nh; ++h) {
+  if ((parts & kPartAddend) && pl.nh > kMaxH) {
+    set_error("hoist::gather: the addend kernel covers at most %d hoisted levels (plan has %d)", kMaxH, pl.nh);
+    return LIST_ENOSYS;
+  }
+  a.nh = pl.nh < kMaxH ? pl.nh : kMaxH;
+  for (int h = 0; h < a.nh; ++h) {
     const size_t R = ctx->vol_res[pl.lev[h]];
     a.pvol[h] = reinterpret_cast<const __nv_bfloat16*>(base + pl.off_pvol[h]) + static_cast<size_t>(image) * R * R * R * kN0;
     a.dstride[h] = static_cast<uint32_t>(static_cast<size_t>(ctx->B) * R * R * R * kN0);
     a.R[h] = static_cast<int>(R);
   }
-  for (int h = pl.nh; h < kMaxH; ++h) { a.pvol[h] = a.pvol[0]; a.dstride[h] = 0; a.R[h] = 1; }
+  for (int h = a.nh; h < kMaxH; ++h) { a.pvol[h] = a.pvol[0]; a.dstride[h] = 0; a.R[h] = 1; }
   a.T = ctx->trans_mat + image * 12;
   a.b0 = w->b0;
   a.X = static_cast<__nv_bfloat16*>(X);

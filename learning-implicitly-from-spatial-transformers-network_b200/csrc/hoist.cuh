@@ -1,26 +1,44 @@
-// Host-side interface of hoist.cu (hoisted fc_0 for dense grids, bf16 mode), shared with api.cu.
+// Host-side interface of hoist.cu / lines.cu (hoisted fc_0 for dense grids, bf16 mode), shared with api.cu and grid_tc.cu.
 #pragma once
 #include "common.cuh"
 
 namespace list {
 namespace hoist {
 
-constexpr int kMaxH = 2;            // hoisted voxel levels
+constexpr int kMaxH = 2;            // hoisted voxel levels of the addend-kernel path (hoist_addend_kernel keeps them in registers)
+constexpr int kMaxLev = 3;          // hoisted voxel levels of the line-table path (lines.cu + grid_tc.cu)
 
 struct Plan {                       // what is hoisted and where it lives in the caller's buffer
   int nh;
-  int lev[kMaxH];
+  int lev[kMaxLev];
   int hoist_cols;                   // leading columns of the full row replaced by the addend
-  int k_h;                          // hoisted row width (multiple of 64)
-  size_t off_pmap, off_pvol[kMaxH], total;
+  int k_h;                          // hoisted row width (multiple of 64): 512 addend columns + the remaining ones
+  size_t off_pmap, off_pvol[kMaxLev], off_zero, total;
+  // line tables (lines.cu): per z-line `rpl` rows of 512 bf16; level h starts at row rowbase[h], class c at + c * R
+  int rpl, rowbase[kMaxLev];
 };
 
-int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl);
+// max_levels / max_res: how many coarse levels may be hoisted and up to which resolution (2 / 16 for the addend-kernel
+// path, 3 / 32 for the line-table path)
+int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl, int max_levels = kMaxH, int max_res = 16);
 int check_gather(const ListCtx* ctx, const Plan& pl, int res);
 int prepare(const ListCtx* ctx, const ListWeights* w, const Plan& pl, void* buf, cudaStream_t st);
 int gather(const ListCtx* ctx, const ListWeights* w, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max,
            int64_t begin, int64_t count, void* X, int64_t ldx, int parts, cudaStream_t st);
 constexpr int kPartAddend = 1, kPartRest = 2;      // `parts` bit mask: which of the two gather kernels to launch
 
+// lines.cu: per-line column tables G[line - line0][rpl][512] of the hoisted levels for the z-lines touched by
+// grid points [begin, begin + count) of image `image`
+size_t lines_bytes(const Plan& pl, int res, int64_t begin, int64_t count);
+int lines(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max, int64_t begin,
+          int64_t count, void* G, cudaStream_t st);
+
 }  // namespace hoist
+
+// grid_tc.cu: fused interpolation + MLP over the rows of grid points [begin, begin + count): Xr = the non-hoisted columns
+// [count][ldx] (hoist::gather with kPartRest on a pointer shifted by -512 columns), G = hoist::lines of the same range
+int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, const void* hoist_buf, int image, int res,
+                double bb_min, double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G, float* sdf,
+                float out_div, float* dbg1, long long* trace, cudaStream_t st);
+
 }  // namespace list

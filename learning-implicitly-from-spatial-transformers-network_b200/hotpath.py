@@ -285,6 +285,69 @@ class HoistedState:
         return X
 
 
+class LineTableState:
+    """The stages of the line-table dense-grid path (csrc/lines.cu + csrc/grid_tc.cu; what list_sdf_grid runs for bf16)
+    exposed one by one for tests and per-kernel timing: projection once per image, then per range of grid points the
+    per-line column tables G, the non-hoisted feature columns Xr and the fused interpolation + MLP kernel."""
+
+    def __init__(self, ctx: HotPathContext, weights: KernelWeights):
+        dev = _require_cuda(ctx.maps_cl, weights.w0)
+        lib = _C.lib()
+        self.ctx, self.base, self.dev = ctx, weights, dev
+        cs, ws = ctx.struct(), weights.struct()
+        need = lib.list_lines_hoist_bytes(C.byref(cs), C.byref(ws))
+        if need == 0:
+            raise RuntimeError("list_lines_hoist_bytes returned 0: this configuration has no line-table path")
+        hc, kf, rpl = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        _C.check(lib.list_lines_layout(C.byref(cs), C.byref(ws), C.byref(hc), C.byref(kf), C.byref(rpl)), "list_lines_layout")
+        self.hoist_cols, self.k_f, self.rows_per_line = hc.value, kf.value, rpl.value
+        self.buf = torch.empty(need, device=dev, dtype=torch.uint8)
+        with torch.cuda.device(dev):
+            _C.check(lib.list_lines_prepare(C.byref(cs), C.byref(ws), self.buf.data_ptr(), need, _stream()), "list_lines_prepare")
+
+    def table(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """G (lines, rows_per_line, 512) bf16 for the z-lines touched by grid points [begin, begin+count)."""
+        cs, ws = self.ctx.struct(), self.base.struct()
+        lib = _C.lib()
+        need = lib.list_lines_table_bytes(C.byref(cs), C.byref(ws), res, begin, count)
+        lines = need // (self.rows_per_line * 1024)
+        G = out if out is not None else torch.empty(lines, self.rows_per_line, 512, device=self.dev, dtype=torch.bfloat16)
+        with torch.cuda.device(self.dev):
+            _C.check(lib.list_lines_table(C.byref(cs), C.byref(ws), self.buf.data_ptr(), image, res, bb_min, bb_max, begin, count,
+                                          G.data_ptr(), G.numel() * 2, _stream()), "list_lines_table")
+        return G
+
+    def rest(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Xr (count, k_f) bf16: the feature columns that are not hoisted."""
+        X = out if out is not None else torch.empty(count, self.k_f, device=self.dev, dtype=torch.bfloat16)
+        cs, ws = self.ctx.struct(), self.base.struct()
+        with torch.cuda.device(self.dev):
+            _C.check(_C.lib().list_lines_rest(C.byref(cs), C.byref(ws), image, res, bb_min, bb_max, begin, count, X.data_ptr(),
+                                              X.stride(0), _stream()), "list_lines_rest")
+        return X
+
+    def evaluate(self, image: int, res: int, begin: int, count: int, Xr: torch.Tensor, G: torch.Tensor, out_div: float = 1.0,
+                 bb_min: float = -0.5, bb_max: float = 0.5, debug: bool = False, trace: bool = False):
+        """Fused interpolation + MLP.  Returns sdf (count,) [, relu(fc_0) (count, 512) fp32] [, trace (16, 12) int64]."""
+        sdf = torch.empty(count, device=self.dev, dtype=torch.float32)
+        h1 = torch.zeros(count, 512, device=self.dev, dtype=torch.float32) if debug else None
+        tr = torch.zeros(16, 12, device=self.dev, dtype=torch.int64) if trace else None
+        cs, ws = self.ctx.struct(), self.base.struct()
+        with torch.cuda.device(self.dev):
+            _C.check(_C.lib().list_grid_tc_fwd(C.byref(cs), C.byref(ws), self.buf.data_ptr(), image, res, bb_min, bb_max, begin, count,
+                                               Xr.data_ptr(), Xr.stride(0), G.data_ptr(), sdf.data_ptr(), float(out_div),
+                                               None if h1 is None else h1.data_ptr(), None if tr is None else tr.data_ptr(),
+                                               _stream()), "list_grid_tc_fwd")
+        out = [sdf]
+        if debug:
+            out.append(h1)
+        if trace:
+            out.append(tr)
+        return out[0] if len(out) == 1 else tuple(out)
+
+
 def mlp(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0, return_workspace: bool = False):
     """Row a-6 on feature rows X (rows, ldx)."""
     dev = _require_cuda(X, weights.w0)
