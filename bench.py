@@ -5,8 +5,8 @@ NCCL gather).
 
     python bench.py [--gpus N --steps K --warmup W] [--impl reference]
 
-A "step" = one pass of the hot path (fused gather + implicit MLP, every chunk) over the whole
-grid of one synthetic image.  One JSON line is printed by rank 0 (see the keys at the bottom).
+A "step" = one pass of the hot path (projection, per chunk: line tables + non-hoisted feature columns
++ the fused interpolation / implicit-MLP kernel) over the whole grid of one synthetic image.  One JSON line is printed by rank 0 (see the keys at the bottom).
 `--impl reference` times the reference's own CPU implementation of the path (the ATen-op port in
 oracle/ref_port.py -- the Python reference cannot travel to the GPU box) on the host cores.
 """
@@ -42,10 +42,11 @@ def parse():
     ap.add_argument("--chunk", type=int, default=0,
                     help="feature rows per gather/MLP launch; 0 = a quarter of the rank's shard, clamped to [262144, 4194304] "
                          "(large launches amortise the last partial wave of gather CTAs, four chunks keep the pipeline busy)")
-    ap.add_argument("--cpu-chunks", type=int, default=2, help="65536-point chunks timed for cpu_baseline")
+    ap.add_argument("--cpu-chunks", type=int, default=3, help="65536-point chunks timed for cpu_baseline (after one warm-up chunk)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-fused", action="store_true", help="bf16: chunked gather + MLP kernels instead of the fused kernel")
+    ap.add_argument("--no-random-T", action="store_true", help="skip the second timing with the random-init transform matrix")
+    ap.add_argument("--trans", default="camera", choices=["camera", "random"], help="transform matrix of the headline run")
     return ap.parse_args()
 
 
@@ -101,7 +102,7 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_rate(res: int, chunks: int, warm: int = 0):
+def cpu_reference_rate(res: int, chunks: int, warm: int = 1):
     """Times the reference's CPU path (ATen-op port, all host threads) on `chunks` 65536-point chunks of
     the same grid / same synthetic image.  Returns (queries/s, cores, sample description)."""
     import torch
@@ -122,7 +123,8 @@ def cpu_reference_rate(res: int, chunks: int, warm: int = 0):
             ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
             n += p.shape[1]
         dt = time.perf_counter() - t0
-    return n / dt, cores, f"first {chunks} x {CPU_CHUNK}-point chunks of the {res}^3 grid, fp32, torch CPU {cores} threads"
+    return n / dt, cores, (f"{chunks} x {CPU_CHUNK}-point chunks of the {res}^3 grid after {warm} warm-up chunk(s), fp32, "
+                           f"torch CPU {cores} threads")
 
 
 def run_reference(a):
@@ -162,10 +164,6 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
-    if a.no_fused:
-        os.environ["LIST_B200_NO_FUSED"] = "1"
-    fused = (a.dtype == "bf16" and os.environ.get("LIST_B200_NO_FUSED", "0") != "1"
-             and os.environ.get("LIST_B200_FUSED", "0") == "1")
 
     import torch
     import torch.distributed as dist
@@ -180,50 +178,65 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     res, total = a.res, a.res ** 3
-    inp = synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans="camera")   # same image on every rank
-    g = inp.to(dev)
-    ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, a.dtype)
-    kw = hotpath.prepare_weights(g.weights, ctx.layout, a.dtype)
-    lay = ctx.layout
     begin, count = parallel.shard_range(total, rank, world, align=res * res)
     auto_chunk = min(4194304, max(262144, -(-(-(-count // 4)) // 65536) * 65536))
     chunk = max(1, min(a.chunk if a.chunk > 0 else auto_chunk, count))
-    cs, wsn = ctx.struct(), kw.struct()
-    ws = hotpath._workspace(cs, wsn, chunk, dev)
-    local_out = torch.empty(1, count, device=dev, dtype=torch.float32)
     n_chunks = -(-count // chunk)
-
-    def step():
-        hotpath.grid_sdf(ctx, kw, res, begin, count, SDF_SCALE, chunk, out=local_out, workspace=ws)
-        if world > 1:
-            return parallel.gather_shards(local_out, total, world, align=res * res)
-        return local_out
 
     def sync():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(a.warmup, 3)):
-        step()
-    sync()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sync()
-    e0.record()
-    for _ in range(a.steps):
-        full = step()
-    e1.record()
-    sync()
-    clocks = sampler.stop() if sampler else None
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_total = ms.item()
-    value = total * a.steps / (ms_total * 1e-3)
-    checksum = float(full.double().sum().item())
+    def timed_run(trans, steps, warmup, sample_clocks):
+        """value / ms per step of the resident path for one transform matrix; returns the objects for the later legs."""
+        inp = synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans=trans)   # same image on every rank
+        g = inp.to(dev)
+        ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, a.dtype)
+        kw = hotpath.prepare_weights(g.weights, ctx.layout, a.dtype)
+        ws = hotpath._workspace(ctx.struct(), kw.struct(), chunk, dev)
+        local_out = torch.empty(1, count, device=dev, dtype=torch.float32)
+
+        def step():
+            hotpath.grid_sdf(ctx, kw, res, begin, count, SDF_SCALE, chunk, out=local_out, workspace=ws)
+            if world > 1:
+                return parallel.gather_shards(local_out, total, world, align=res * res)
+            return local_out
+
+        for _ in range(max(warmup, 3)):
+            step()
+        sync()
+        sampler = ClockSampler(local) if (rank == 0 and sample_clocks) else None
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        e0.record()
+        for _ in range(steps):
+            full = step()
+        e1.record()
+        sync()
+        clocks = sampler.stop() if sampler else None
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = ms.item()
+        return {"inp": inp, "ctx": ctx, "kw": kw, "ws": ws, "local_out": local_out, "ms_total": ms_total,
+                "value": total * steps / (ms_total * 1e-3), "clocks": clocks, "checksum": float(full.double().sum().item())}
+
+    main_run = timed_run(a.trans, a.steps, a.warmup, True)
+    inp, ctx, kw, ws, local_out = (main_run[k] for k in ("inp", "ctx", "kw", "ws", "local_out"))
+    lay = ctx.layout
+    ms_total, value, clocks, checksum = main_run["ms_total"], main_run["value"], main_run["clocks"], main_run["checksum"]
+    other_T = None
+    if not a.no_random_T:
+        # SURVEY.md 8d "report both": what a random-init spatial transformer emits (about half of the queries clamp, the
+        # divide's singular plane cuts the grid)
+        tname = "random" if a.trans == "camera" else "camera"
+        r2 = timed_run(tname, a.steps, a.warmup, False)
+        other_T = {"trans_mat": "random-init" if tname == "random" else "camera-like", "value": r2["value"], "unit": UNIT,
+                   "ms_per_step": r2["ms_total"] / a.steps, "steps": a.steps, "checksum": r2["checksum"]}
+        del r2
 
     # ---- per-kernel timing for the roofline (same stream, CUDA events, after the timed region) ----
     pk = peaks()
@@ -232,100 +245,126 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath))
+
     def traffic_of(name):
         """dram bytes of one launch of `name` (ncu capture in profiles/, scaled to this run's rows per launch)."""
         e = traffic.get(name)
         if isinstance(e, dict) and e.get("rows"):
             return e["dram_bytes"] / e["rows"] * chunk
         return None
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]   # fused-kernel timing below
-    roof_fused = None
-    if fused:
-        # the step IS one kernel launch (sdf_fused_kernel): time it alone
-        tf = []
-        for rep in range(3):
-            ev[0].record()
-            hotpath.grid_sdf(ctx, kw, res, begin, count, SDF_SCALE, chunk, out=local_out, workspace=ws)
-            ev[1].record()
-            torch.cuda.synchronize()
-            tf.append(ev[0].elapsed_time(ev[1]))
-        t_fused = sorted(tf)[1]
-        fl = FLOP_PER_QUERY * count / (t_fused * 1e-3) / 1e12
-        roof_fused = {"kernel": "sdf_fused_kernel", "bound": "tensor", "achieved": fl, "peak": pk["tensor"],
-                      "unit": "TFLOP/s", "frac": fl / pk["tensor"], "traffic": traffic_of("sdf_fused_kernel"),
-                      "ms_per_step": t_fused, "launches_per_step": 1, "peak_source": pk["src"],
-                      "note": "gather fused into the MLP kernel: feature rows never reach HBM, compulsory HBM bytes "
-                              "are 4 B/query of SDF + one read of the per-image tensors; reported against the "
-                              "tensor-core roofline only (SURVEY.md 8d)"}
-        os.environ["LIST_B200_NO_FUSED"] = "1"            # the unfused pair below, for comparison
-    hoisted = (a.dtype == "bf16" and not fused and os.environ.get("LIST_B200_HOIST", "1") != "0")
-    hs = None
-    if hoisted:
-        try:
-            hs = hotpath.HoistedState(ctx, kw)            # what list_sdf_grid builds at the start of every call
-        except RuntimeError:
-            hoisted = False
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    t_add = t_rest = t_mlp = 0.0
+
+    nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+    path = "plain"
+    if a.dtype == "bf16" and os.environ.get("LIST_B200_HOIST", "1") != "0":
+        path = "lines" if os.environ.get("LIST_B200_LINES", "1") != "0" else "addend"
+    state = None
+    try:
+        if path == "lines":
+            state = hotpath.LineTableState(ctx, kw)        # what list_sdf_grid builds at the start of every call
+        elif path == "addend":
+            state = hotpath.HoistedState(ctx, kw)
+    except RuntimeError:
+        path = "plain"
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    stats = torch.zeros(2, device=dev, dtype=torch.int64)
+    t_a = t_b = t_mlp = t_plan = 0.0
     for rep in range(2):                                   # rep 0 warms the allocator
-        ta = tr = tm = 0.0
+        ta = tb = tm = tp = 0.0
+        stats.zero_()
         for n0 in range(0, count, chunk):
             n = min(chunk, count - n0)
-            if hoisted:
-                X = torch.empty(n, hs.k_h, device=dev, dtype=torch.bfloat16)
+            if path == "lines":
                 ev[0].record()
-                hs.gather_grid(0, res, begin + n0, n, parts=1, out=X)      # hoist_addend_kernel
+                G = state.table(0, res, begin + n0, n)                          # hoist_lines_kernel
                 ev[1].record()
-                hs.gather_grid(0, res, begin + n0, n, parts=2, out=X)      # hoist_rest_kernel
+                X = state.rest(0, res, begin + n0, n)                           # hoist_rest_kernel
+                ev[4].record()
+                plan = state.plan(0, res, begin + n0, n, G)                     # grid_plan_kernel
+                ev[2].record()
+                state.evaluate(res, begin + n0, n, X, plan, SDF_SCALE, stats=stats)   # grid_tc_kernel
+            elif path == "addend":
+                X = torch.empty(n, state.k_h, device=dev, dtype=torch.bfloat16)
+                ev[0].record()
+                state.gather_grid(0, res, begin + n0, n, parts=1, out=X)      # hoist_addend_kernel
+                ev[1].record()
+                state.gather_grid(0, res, begin + n0, n, parts=2, out=X)      # hoist_rest_kernel
+                ev[2].record()
+                state.mlp(X, SDF_SCALE)
             else:
                 ev[0].record()
                 ev[1].record()
                 X = hotpath.gather_grid_features(ctx, 0, res, begin + n0, n)
-            ev[2].record()
-            if hoisted:
-                hs.mlp(X, SDF_SCALE)
-            else:
+                ev[2].record()
                 hotpath.mlp(kw, X, SDF_SCALE)
             ev[3].record()
             torch.cuda.synchronize()
             ta += ev[0].elapsed_time(ev[1])
-            tr += ev[1].elapsed_time(ev[2])
+            if path == "lines":
+                tb += ev[1].elapsed_time(ev[4])
+                tp += ev[4].elapsed_time(ev[2])
+                del G, plan
+            else:
+                tb += ev[1].elapsed_time(ev[2])
             tm += ev[2].elapsed_time(ev[3])
             del X
-        t_add, t_rest, t_mlp = ta, tr, tm
-    if fused:
-        os.environ.pop("LIST_B200_NO_FUSED", None)
-    nbytes = lambda ts: sum(t.numel() * t.element_size() for t in ts)
+        t_a, t_b, t_mlp, t_plan = ta, tb, tm, tp
     roofs = []
-    if hoisted:
-        # hoisted fc_0 (csrc/hoist.cu): the per-query GEMM runs on 512 addend + (k_out - hoist_cols) feature columns
-        hoist_cols = hs.hoist_cols
-        k_eff = 512 + lay.k_out - hoist_cols                   # columns of the hoisted row that carry data
-        k_mma = lay.k_out - hoist_cols                         # fc_0's K on the tensor cores; the addend is added in its epilogue
-        flop_exec = 2 * (k_mma * 512 + 512 * 256 + 256 * 256 + 256) + 512
+    launches_per_step = n_chunks * 2
+    if path == "lines":
+        hoist_cols, k_f = state.hoist_cols, state.k_f
+        k_dense = lay.k_out - hoist_cols                                       # real (unpadded) columns of the dense part
+        pair_tiles, i_chunks = (int(x) for x in stats.cpu())
+        flop_dense = 2 * (k_dense * 512 + 512 * 256 + 256 * 256 + 256)
+        flop_interp = 2 * 512 * 64 * i_chunks * 256 / count                     # [256 x 64] x [64 x 512] per chunk and tile pair
+        flop_exec = flop_dense + flop_interp
         hoisted_levels = [l for l in range(len(ctx.vols_cl)) if lay.vol_off[l] < hoist_cols and ctx.vol_ch[l] % 8 == 0]
-        proj_bytes = hs.buf.numel()                                           # projected maps + coarse volumes
+        lines_touched = (begin + count - 1) // res - begin // res + 1
+        g_bytes = lines_touched * state.rows_per_line * 1024
+        proj_bytes = state.buf.numel() - ctx.B * 137 * 137 * 512 * 2           # projected volumes (the map is read by grid_tc)
         rest_vol_bytes = nbytes([v for l, v in enumerate(ctx.vols_cl) if l not in hoisted_levels])
-        mlp_note = (f"hoisted fc_0: {hoist_cols} of {lay.k_out} K columns (maps + levels {hoisted_levels}) are projected "
-                    "through W0 once per image, sampled as one 512-wide addend block and added in fc_0's epilogue; "
-                    "`achieved` counts EXECUTED flops "
-                    f"({flop_exec}/query), `effective` the reference's algorithmic {FLOP_PER_QUERY}/query")
-        gathers = [("hoist_addend_kernel", t_add, count * 512 * es + proj_bytes,
+        mlp_note = (f"line-table path: {hoist_cols} of {lay.k_out} K columns (maps + levels {hoisted_levels}) are projected through W0 "
+                    f"once per image; per tile of 128 steps their interpolation runs as {i_chunks / max(pair_tiles, 1):.2f} extra "
+                    "[256 x 64] x [64 x 512] MMA chunks per tile pair (sparse weights x rows of the projected map / line tables) "
+                    f"next to the dense K = {k_dense} part.  `achieved` counts EXECUTED tensor-core flops "
+                    f"({flop_dense} dense + {flop_interp:.0f} interpolation per query), `achieved_dense_only` the dense part alone, "
+                    f"`effective` the reference's algorithmic {FLOP_PER_QUERY}/query")
+        mlp_name = "grid_tc_kernel"
+        gathers = [("hoist_lines_kernel", t_a, g_bytes + proj_bytes,
+                    f"writes the per-line column tables ({state.rows_per_line} rows x 512 bf16 per z-line); reads the projected volumes once"),
+                   ("hoist_rest_kernel", t_b, count * k_dense * es + rest_vol_bytes,
+                    f"writes the {k_dense} non-hoisted feature columns; reads the fine volumes once"),
+                   ("grid_plan_kernel", t_plan, pair_tiles * 2 * (24 * 128 * 4 + 8 * 64 * i_chunks / max(2 * pair_tiles, 1)),
+                    "index work: per tile of 128 steps the list of source rows and 24 x 128 weight entries (bytes written)")]
+        launches_per_step = 4 + 4 * n_chunks
+    elif path == "addend":
+        hoist_cols = state.hoist_cols
+        k_eff = 512 + lay.k_out - hoist_cols
+        k_mma = lay.k_out - hoist_cols
+        flop_exec = 2 * (k_mma * 512 + 512 * 256 + 256 * 256 + 256) + 512
+        flop_dense = flop_exec
+        hoisted_levels = [l for l in range(len(ctx.vols_cl)) if lay.vol_off[l] < hoist_cols and ctx.vol_ch[l] % 8 == 0]
+        proj_bytes = state.buf.numel()
+        rest_vol_bytes = nbytes([v for l, v in enumerate(ctx.vols_cl) if l not in hoisted_levels])
+        mlp_note = (f"round-1 addend path: {hoist_cols} of {lay.k_out} K columns are projected once per image, sampled as one "
+                    f"512-wide addend block and added in fc_0's epilogue; `achieved` counts EXECUTED flops ({flop_exec}/query)")
+        mlp_name = "mlp_tc_kernel"
+        gathers = [("hoist_addend_kernel", t_a, count * 512 * es + proj_bytes,
                     "writes the 512 addend columns; reads the projected maps / coarse volumes once"),
-                   ("hoist_rest_kernel", t_rest, count * (k_eff - 512) * es + rest_vol_bytes,
+                   ("hoist_rest_kernel", t_b, count * (k_eff - 512) * es + rest_vol_bytes,
                     f"writes the remaining {k_eff - 512} feature columns; reads the fine volumes once")]
+        launches_per_step = 3 + 3 * n_chunks
     else:
-        flop_exec, mlp_note = FLOP_PER_QUERY, None
-        generic = os.environ.get("LIST_B200_GRID_GENERIC", "0") == "1"
-        gathers = [("gather_fwd_kernel" if generic else "gather_grid_kernel", t_rest,
-                    count * lay.k_out * es + nbytes([ctx.maps_cl, *ctx.vols_cl]),        # SURVEY.md §8d (q generated in-kernel)
+        flop_exec = flop_dense = FLOP_PER_QUERY
+        mlp_note = None
+        mlp_name = "mlp_tc_kernel" if a.dtype == "bf16" else "sgemm_kernel"
+        gathers = [("gather_grid_kernel", t_b, count * lay.k_out * es + nbytes([ctx.maps_cl, *ctx.vols_cl]),   # SURVEY.md 8d
                     "writes the full 3610-column feature row")]
     mlp_tflops = flop_exec * count / (t_mlp * 1e-3) / 1e12
-    roof_mlp = {"kernel": "mlp_tc_kernel" if a.dtype == "bf16" else "sgemm_kernel", "bound": "tensor",
-                "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": mlp_tflops / pk["tensor"],
-                "traffic": traffic_of("mlp_tc_kernel"), "ms_per_step": t_mlp, "launches_per_step": n_chunks,
-                "flop_per_query": flop_exec, "effective": FLOP_PER_QUERY * count / (t_mlp * 1e-3) / 1e12,
-                "peak_source": pk["src"]}
+    roof_mlp = {"kernel": mlp_name, "bound": "tensor", "achieved": mlp_tflops, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": mlp_tflops / pk["tensor"], "traffic": traffic_of(mlp_name), "ms_per_step": t_mlp,
+                "launches_per_step": n_chunks, "flop_per_query": flop_exec,
+                "achieved_dense_only": flop_dense * count / (t_mlp * 1e-3) / 1e12,
+                "effective": FLOP_PER_QUERY * count / (t_mlp * 1e-3) / 1e12, "peak_source": pk["src"]}
     if mlp_note:
         roof_mlp["note"] = mlp_note
     roofs.append(roof_mlp)
@@ -334,28 +373,8 @@ def main():
         roofs.append({"kernel": name, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
                       "frac": gbs / pk["hbm"], "traffic": traffic_of(name), "ms_per_step": tk,
                       "launches_per_step": n_chunks, "bytes_per_step": nb, "what": what, "peak_source": pk["src"]})
-    if hoisted:
-        # SURVEY.md 8d's accounting for "the gather" as a whole: one full feature row (k_out columns) per query + one read
-        # of the per-image tensors, over the time of the two kernels that now do that job.  The kernels move fewer bytes
-        # than that because fc_0's projection is hoisted; both views are reported.
-        t_g = t_add + t_rest
-        alg = count * lay.k_out * es + nbytes([ctx.maps_cl, *ctx.vols_cl])
-        act = sum(g[2] for g in gathers)
-        tg_traffic = [traffic_of(g[0]) for g in gathers]
-        gather_both = {"kernel": "hoist_addend_kernel+hoist_rest_kernel", "bound": "hbm", "achieved": act / (t_g * 1e-3) / 1e9,
-                       "peak": pk["hbm"], "unit": "GB/s", "frac": act / (t_g * 1e-3) / 1e9 / pk["hbm"],
-                       "traffic": sum(tg_traffic) if all(x is not None for x in tg_traffic) else None,
-                       "ms_per_step": t_g, "launches_per_step": 2 * n_chunks, "bytes_per_step": act,
-                       "survey_8d_algorithmic_bytes": alg, "survey_8d_achieved": alg / (t_g * 1e-3) / 1e9,
-                       "survey_8d_frac": alg / (t_g * 1e-3) / 1e9 / pk["hbm"],
-                       "what": "the two gather kernels together; `achieved` counts the bytes they actually have to move, "
-                               "`survey_8d_*` the bytes of the un-hoisted formulation (7220 B/query + per-image tensors)",
-                       "peak_source": pk["src"]}
     roofs.sort(key=lambda r: -r["ms_per_step"])
-    if fused:
-        dominant, other = roof_fused, {"unfused_kernels_for_comparison": roofs}
-    else:
-        dominant, other = roofs[0], roofs[1:] + ([gather_both] if hoisted else [])
+    dominant, other = roofs[0], roofs[1:]
 
     # ---- end to end through the C ABI with HOST buffers (H2D + prep + grid + D2H inside the timed region) ----
     e2e = None
@@ -363,12 +382,11 @@ def main():
         pin = lambda t: t.contiguous().pin_memory()
         runner = parallel.ShardedHostRunner([pin(m) for m in inp.maps], [pin(v) for v in inp.vols], pin(inp.trans_mat), kw,
                                             res, a.dtype, chunk)
-        for _ in range(2):
+        for _ in range(3):
             runner.run(SDF_SCALE)
         sync()
-        e_steps = min(a.steps, 3)
         t0 = time.perf_counter()
-        for _ in range(e_steps):
+        for _ in range(a.steps):
             host_out = runner.run(SDF_SCALE)
             torch.cuda.synchronize()                      # the D2H result is consumed every step
             _ = float(host_out[0, 0])
@@ -376,13 +394,13 @@ def main():
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": total * e_steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
-               "d2h_bytes_per_step": runner.d2h_bytes, "steps": e_steps,
+        e2e = {"value": total * a.steps / dt.item(), "unit": UNIT, "h2d_bytes_per_step": runner.h2d_bytes,
+               "d2h_bytes_per_step": runner.d2h_bytes, "steps": a.steps,
                "what": "parallel.ShardedHostRunner: pinned host per-image tensors (fp32, reference layout) -> H2D "
                        + ("(1/N of every tensor per rank + one NCCL all_gather over NVLink) " if world > 1 else
-                          "(C ABI list_sdf_grid_host: big volumes upload behind the projection and the first addend "
-                          "gather, every chunk downloads behind the next chunk's kernels) ")
-                       + "-> prep kernels -> projection + gather + MLP over the rank's grid shard -> D2H of its SDF values "
+                          "(C ABI list_sdf_grid_host: the fine volumes upload behind the projection and the first line "
+                          "tables, every chunk downloads behind the next chunk's kernels) ")
+                       + "-> prep kernels -> projection + per-chunk kernels over the rank's grid shard -> D2H of its SDF values "
                        "into pinned host memory; wall clock, max over ranks"}
         # sanity: same numbers as the resident path
         assert torch.equal(host_out, local_out.cpu()), "host path and resident path disagree"
@@ -392,6 +410,12 @@ def main():
         v, cores, sample = cpu_reference_rate(res, a.cpu_chunks)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    kernel_path = {"lines": "projection once per image; per chunk: hoist_lines_kernel (per-line column tables of the projected "
+                            "levels), grid_plan_kernel (row lists + interpolation weights per tile), hoist_rest_kernel "
+                            "(non-hoisted feature columns), grid_tc_kernel (interpolation of the "
+                            "hoisted terms as MMA chunks + fc_0..fc_out, tcgen05/TMEM/TMA)",
+                   "addend": "round-1 path: projection + addend/rest gather + MLP (fc_0 K=832 + addend in the epilogue)",
+                   "plain": "chunked gather + MLP kernels"}[path]
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
@@ -400,14 +424,14 @@ def main():
             "config": {"workload": f"cfg-4: LIST inference, 1 image (224x224 synthetic features), {res}^3 dense SDF grid "
                                    f"sharded by contiguous point ranges over {world} GPU(s) + one NCCL all_gather",
                        "grid_res": res, "queries_per_step": total, "chunk_rows": chunk, "sdf_scale": SDF_SCALE,
-                       "trans_mat": "camera-like", "kernel_path": "fused gather->MLP (sdf_fused_kernel)" if fused else
-                       ("hoisted fc_0: projection + addend/rest gather + MLP (fc_0 K=832 + addend in the epilogue), gather of chunk i+1 "
-                        "overlapped with the MLP of chunk i" if hoisted else "chunked gather + MLP kernels"),
+                       "trans_mat": "camera-like" if a.trans == "camera" else "random-init", "kernel_path": kernel_path,
+                       "inputs": "per-image tensors are seeded random tensors of the shapes the reference's per-image stage emits "
+                                 "(list_b200/synth.py); the kernels' cost does not depend on the values",
                        "l2": "no flush: a step touches 16.8 M distinct queries over 132 MB of per-image tensors + 3.9 MB of "
                              "weights re-streamed per 256-row tile; nothing is reused across steps but those",
                        "parallelism": f"grid-shard x{world}"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * (1 if fused else (n_chunks * 3 + 3 if hoisted else n_chunks * 2)),
-            "roofline": dominant, "roofline_other": other, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * launches_per_step,
+            "roofline": dominant, "roofline_other": other, "other_transform": other_T, "cpu_baseline": cpu,
             "checksum": checksum,
         }), flush=True)
     if world > 1:

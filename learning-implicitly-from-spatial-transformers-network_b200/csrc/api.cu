@@ -154,8 +154,8 @@ static bool hoist_enabled() {
 // Line-table path (lines.cu + grid_tc.cu): the hoisted terms are interpolated on the tensor cores inside the MLP kernel.
 // Default for bf16 dense grids; LIST_B200_LINES=0 selects the round-1 addend-kernel path (A/B aid).
 static bool lines_enabled() {
-  static const bool on = []() { const char* e = getenv("LIST_B200_LINES"); return !(e && e[0] == '0'); }();
-  return on;
+  const char* e = getenv("LIST_B200_LINES");
+  return !(e && e[0] == '0');
 }
 constexpr int kLinesLevels = 3, kLinesMaxRes = 32;     // hoisted levels of the line-table path
 
@@ -539,17 +539,36 @@ int list_lines_rest(const ListCtx* ctx, const ListWeights* w, int32_t image, int
                        hoist::kPartRest, static_cast<cudaStream_t>(stream));
 }
 
-int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res, double bb_min,
-                     double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G, float* sdf, float out_div,
-                     float* dbg_h1, int64_t* trace, void* stream) {
+size_t list_grid_plan_bytes(int32_t res, int64_t begin, int64_t count) {
+  if (res < 1 || begin < 0 || count <= 0) return 0;
+  return grid_plan_bytes(res, begin, count);
+}
+
+int list_grid_plan(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res, double bb_min,
+                   double bb_max, int64_t begin, int64_t count, const void* G, void* plan, size_t plan_bytes, void* stream) {
+  hoist::Plan pl;
+  int rc = lines_plan(ctx, w, &pl, "list_grid_plan");
+  if (rc) return rc;
+  if ((rc = check_range(res, begin, count, "list_grid_plan"))) return rc;
+  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_grid_plan: image %d outside [0,%d)", image, ctx->B);
+  LIST_CHECK_ARG(hoist_buf && G && plan, "list_grid_plan: NULL argument");
+  if (plan_bytes < grid_plan_bytes(res, begin, count)) {
+    set_error("list_grid_plan: plan buffer %zu B < required %zu B", plan_bytes, grid_plan_bytes(res, begin, count));
+    return LIST_ENOMEM;
+  }
+  return grid_plan(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, G, plan, static_cast<cudaStream_t>(stream));
+}
+
+int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count,
+                     const void* Xr, int64_t ldx, const void* plan, float* sdf, float out_div, float* dbg_h1, int64_t* trace,
+                     uint64_t* stats, void* stream) {
   hoist::Plan pl;
   int rc = lines_plan(ctx, w, &pl, "list_grid_tc_fwd");
   if (rc) return rc;
   if ((rc = check_range(res, begin, count, "list_grid_tc_fwd"))) return rc;
-  LIST_CHECK_ARG(image >= 0 && image < ctx->B, "list_grid_tc_fwd: image %d outside [0,%d)", image, ctx->B);
-  LIST_CHECK_ARG(hoist_buf && Xr && G && sdf && out_div != 0.f, "list_grid_tc_fwd: NULL argument or out_div == 0");
-  return grid_tc_fwd(ctx, w, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, Xr, ldx, G, sdf, out_div, dbg_h1,
-                     reinterpret_cast<long long*>(trace), static_cast<cudaStream_t>(stream));
+  LIST_CHECK_ARG(Xr && plan && sdf && out_div != 0.f, "list_grid_tc_fwd: NULL argument or out_div == 0");
+  return grid_tc_fwd(ctx, w, pl, res, bb_min, bb_max, begin, count, Xr, ldx, plan, sdf, out_div, dbg_h1,
+                     reinterpret_cast<long long*>(trace), reinterpret_cast<unsigned long long*>(stats), static_cast<cudaStream_t>(stream));
 }
 
 int list_hoist_gather_grid_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
@@ -673,7 +692,8 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
       hoist::check_gather(ctx, pl3, res) == LIST_OK) {
     const int k_f = pl3.k_h - 512;
     const size_t xr_bytes = align_up(static_cast<size_t>(chunk_rows) * k_f * 2, 256);
-    if (xr_bytes + hoist::lines_bytes(pl3, res, res - 1, chunk_rows) <= xb) {
+    const size_t g_bytes = align_up(hoist::lines_bytes(pl3, res, res - 1, chunk_rows), 256);      // worst case: the chunk starts on a line's last point
+    if (xr_bytes + g_bytes + grid_plan_bytes(res, res - 1, chunk_rows) <= xb) {
       void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
       if ((rc = hoist::prepare(ctx, w, pl3, hbuf, st))) return rc;
       return run_chunks(
@@ -681,8 +701,10 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
           [&](int64_t i, void* X, cudaStream_t s) -> int {
             int b; int64_t n0, n;
             span(i, b, n0, n);
-            int r2 = hoist::lines(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, static_cast<char*>(X) + xr_bytes, s);
+            char* const G = static_cast<char*>(X) + xr_bytes;
+            int r2 = hoist::lines(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, G, s);
             if (r2) return r2;
+            if ((r2 = grid_plan(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, G, G + g_bytes, s))) return r2;
             // the line tables only read the projected tensors; everything uploaded late is first read by the rest kernel
             if (i == 0 && !late_done && hooks && hooks->late && (r2 = hook_late(hooks, s))) return r2;
             return hoist::gather(ctx, w, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, static_cast<__nv_bfloat16*>(X) - 512, k_f,
@@ -691,8 +713,8 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
           [&](int64_t i, void* X, cudaStream_t s) -> int {
             int b; int64_t n0, n;
             span(i, b, n0, n);
-            const int r2 = grid_tc_fwd(ctx, w, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, X, k_f, static_cast<char*>(X) + xr_bytes,
-                                       sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, nullptr, nullptr, s);
+            const int r2 = grid_tc_fwd(ctx, w, pl3, res, bb_min, bb_max, begin + n0, n, X, k_f, static_cast<char*>(X) + xr_bytes + g_bytes,
+                                       sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, nullptr, nullptr, nullptr, s);
             return r2 ? r2 : hook_download(hooks, sdf, static_cast<int64_t>(b) * count + n0, n, s);
           });
     }

@@ -17,17 +17,19 @@
 // block of round 1 (34 GB through HBM per 256^3 grid) no longer exists.
 //
 //   Warp roles : warp 0 = TMA producer and ring allocator, warp 1 = TMEM allocator + MMA issuer (one thread),
-//                warps 2..5 = epilogue (one TMEM lane quarter each), warps 6..9 = interp warps (tile plan, Aw, Brows).
+//                warps 2..5 = epilogue (one TMEM lane quarter each), warps 6..9 = interp warps (Aw, Brows).
 //   CG = 2     : CTA pair, tcgen05.mma.cta_group::2, M = 256.  CTA r evaluates tile 2p + r; the K space of the pair's
 //                I chunks is the concatenation of both tiles' row lists (the other CTA's rows get zero weights), and each
 //                CTA copies ITS half of the 512 channels of every listed row (B operand split along N).
 //   Ring       : 12 units of 16 KB, allocated first-in first-out by the TMA thread in consumption order
-//                  F chunk [X box | W0 box | W0 box] -> I chunk [Aw | Brows j=0 | Brows j=1] -> 8 + 4 weight boxes of fc_1 / fc_2.
-//                I chunks are filled by the interp warps once the allocator has granted their units (grant barriers).
-//   Row lists  : built per tile by the interp warps ("plan"): voxel rows = contiguous node ranges of the line table per
-//                (level, class); pixel rows = the nodes of the pixel cells the tile's path crosses, de-duplicated between
-//                consecutive cells (a node shared with the previous cell keeps its slot).  Both CTAs of a pair build
-//                both plans (deterministic), so they agree on the chunk count without communicating.
+//                  I chunk [Aw | Brows j=0 | Brows j=1] -> F chunk [X box | W0 box | W0 box] -> 8 + 4 weight boxes of fc_1 / fc_2.
+//                I chunks are filled by the interp warps once the allocator has granted their units (grant barriers); they
+//                come first in a tile's sequence so that they are granted and filled during the previous tile's fc_1 / fc_2.
+//   Tile plans : grid_plan_kernel (one CTA per tile, launched before this kernel) writes per tile the list of source rows
+//                (absolute addresses; voxel rows = contiguous node ranges of the line table per (level, class); pixel rows
+//                = the nodes of the pixel cells the tile's path crosses, de-duplicated between consecutive cells) and per
+//                step its <= 22 (chunk, position, bf16 weight) entries.  Planning is serial, latency-bound index work; as
+//                its own kernel it runs at full occupancy instead of on four warps next to the MMA pipeline.
 #include <cstdlib>
 
 #include "grid_common.cuh"
@@ -53,33 +55,45 @@ constexpr int kThreads = (kIntWarp0 + kIntWarps) * 32;   // 320
 constexpr int kMaxLev = hoist::kMaxLev;
 constexpr int NC = kMaxLev * 3;                    // (level, W-shift class) combinations
 constexpr int kEnt = 2 * NC + 4;                   // weight entries of a step: two per combination + 4 pixel taps
+constexpr int kEntPad = 24;                        // row pitch of the entry table (six 16-byte vectors)
+static_assert(kEnt <= kEntPad, "entry table row");
 constexpr int kMaxRows = 832;                      // rows of one tile's list: <= 3 * sum R voxel + 4 * 128 pixel, 64-aligned
-constexpr uint32_t kEmpty = 0xffff0000u;           // weight entry that matches no chunk
-constexpr uint32_t kKindG = 0u, kKindPix = 1u << 30, kKindZero = 2u << 30, kIdxMask = (1u << 30) - 1;
+constexpr uint32_t kEmpty = 0xff800000u;           // weight entry that matches no chunk
+// weight entry: chunk << 23 | byte offset inside the row's 128 B of the (128B-swizzled, K-major) Aw unit << 16 | bf16 weight
 
-// ---- shared-memory carve-up (offsets from the 1024-byte aligned base) ----
+// ---- tile plans in global memory (grid_plan_kernel -> grid_tc_kernel) ----
+constexpr int kPlanRowBytes = kMaxRows * 8;        // uint64 source address per listed row
+constexpr int kPlanEntBytes = BM * kEntPad * 4;    // uint32 entries [128 steps][kEntPad]
+struct PlanBuf {
+  int* hdr;                         // [n_tiles] 64-row chunks of the tile's list (0: tile outside the launch's range)
+  unsigned long long* rows;         // [n_tiles][kMaxRows]
+  uint32_t* ent;                    // [n_tiles][128][kEntPad]
+};
+inline size_t plan_hdr_bytes(unsigned n_tiles) { return (static_cast<size_t>(n_tiles) * 4 + 255) / 256 * 256; }
+inline size_t plan_bytes(unsigned n_tiles) {
+  return plan_hdr_bytes(n_tiles) + static_cast<size_t>(n_tiles) * (kPlanRowBytes + kPlanEntBytes);
+}
+inline PlanBuf plan_carve(void* buf, unsigned n_tiles) {
+  char* b = static_cast<char*>(buf);
+  PlanBuf pb;
+  pb.hdr = reinterpret_cast<int*>(b);
+  pb.rows = reinterpret_cast<unsigned long long*>(b + plan_hdr_bytes(n_tiles));
+  pb.ent = reinterpret_cast<uint32_t*>(b + plan_hdr_bytes(n_tiles) + static_cast<size_t>(n_tiles) * kPlanRowBytes);
+  return pb;
+}
+
+// ---- shared-memory carve-up of grid_tc_kernel (offsets from the 1024-byte aligned base) ----
 constexpr int OFF_PAR = NU * UNIT_BYTES;                           // b0 b1 b2 w3 (fp32)
 constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;
-constexpr int OFF_ENT = OFF_PAR + PARAM_FLOATS * 4;                // uint32 [128][kEnt]: slot << 16 | bf16 weight
-constexpr int OFF_ROWS = OFF_ENT + BM * kEnt * 4;                  // uint32 [2][kMaxRows]: kind | row index
-constexpr int OFF_KEY = OFF_ROWS + 2 * kMaxRows * 4;               // int [128] pixel cell of a step (-1: none)
-constexpr int OFF_CKEY = OFF_KEY + BM * 4;                         // int [128] cell -> key
-constexpr int OFF_CBASE = OFF_CKEY + BM * 4;                       // int [128] cell -> first new slot
-constexpr int OFF_CMASK = OFF_CBASE + BM * 4;                      // int [128] cell -> new mask | valid mask << 4
-constexpr int OFF_CSLOT = OFF_CMASK + BM * 4;                      // short [128][4] cell -> slot of its 4 nodes
-constexpr int OFF_MISC = OFF_CSLOT + BM * 4 * 2;                   // int first[NC] last[NC] scan[8] plan[2][2]
-constexpr int MISC_INTS = 2 * NC + 8 + 4 + 2;
-constexpr int OFF_BAR = (OFF_MISC + MISC_INTS * 4 + 7) / 8 * 8;
-constexpr int NUM_BARS = 3 * NB + 2 + 2;                           // full empty grant | dfull hready | plan[2]
+constexpr int OFF_ENT = OFF_PAR + PARAM_FLOATS * 4;                // this CTA's tile: uint32 [128][kEntPad]
+constexpr int OFF_ROWS = OFF_ENT + kPlanEntBytes;                  // uint64 [2][kMaxRows]: both tiles' row lists
+constexpr int OFF_BAR = OFF_ROWS + 2 * kPlanRowBytes;
+constexpr int NUM_BARS = 4 * NB + 2;                               // full empty grant ifull | dfull hready
 constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
-struct Params {
-  const float *b0, *b1, *b2, *w3, *b3;
-  float* sdf;                       // [count] of this image
-  float out_div;
-  int nkF;                          // F chunks: (k_pad - hoist_cols) / 64
-  int x_rows;                       // rows of the X map (= count)
+// geometry of the interpolated terms, shared by the plan kernel and the fused kernel
+struct Geo {
   TileMap tm;
   unsigned n_tiles;
   const __nv_bfloat16* pmap;        // projected map of the image [S*S][512]
@@ -88,8 +102,19 @@ struct Params {
   const float* T;
   int S, nh, rpl;
   int R[kMaxLev], rowbase[kMaxLev];
+};
+
+struct Params {
+  const float *b0, *b1, *b2, *w3, *b3;
+  float* sdf;                       // [count] of this image
+  float out_div;
+  int nkF;                          // F chunks: (k_pad - hoist_cols) / 64
+  TileMap tm;
+  unsigned n_tiles;
+  PlanBuf plan;
   float* dbg1;                      // optional [count][512]: relu(fc_0) in fp32 before rounding
   long long* trace;
+  unsigned long long* stats;        // optional [2]: += pair tiles, += I chunks (executed-FLOP accounting of bench.py)
   uint32_t b_lbo, b_sbo, b_kadv;    // MN-major descriptor of the Brows units: bytes between 64-channel groups / 8-row groups / 16 k rows
 };
 
@@ -119,7 +144,7 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
 }
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
@@ -133,10 +158,10 @@ __device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) 
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHint)
       : "memory");
   return ok != 0;
 }
@@ -154,33 +179,21 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
 }
 __device__ __forceinline__ uint32_t bf16_bits(float x) { return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(x))); }
 
-// ------------------------------------------------------------------ tile plan (interp warps, 128 threads, thread = step)
-struct PlanSmem {
-  uint32_t* ent;      // [128][kEnt]
-  uint32_t* rows;     // [2][kMaxRows]
-  int* key;           // [128]
-  int* ckey;          // [128]
-  int* cbase;         // [128]
-  int* cmask;         // [128]
-  short* cslot;       // [128][4]
-  int* first;         // [NC]
-  int* last;          // [NC]
-  int* scan;          // [8]
-};
-
-__device__ __forceinline__ void ibar() { named_bar_sync(2, kIntWarps * 32); }
-
-// Builds list L (rows of tile `tile`) and, if `own`, the weight entries of this CTA's 128 steps.  Returns the number of
-// 64-row chunks of the list.  All 128 interp threads call it with the same arguments.
-__device__ __noinline__ int plan_list(const Params& p, const PlanSmem& sm, unsigned tile, int L, bool own, int it) {
+// ------------------------------------------------------------------ tile plans
+// One CTA of 128 threads per tile, thread = step.  Writes hdr[tile] (64-row chunks), rows[tile][..] (source address of
+// every listed row, padded with the zero row to a whole chunk) and ent[tile][step][..] (weight entries).
+__global__ void __launch_bounds__(BM) grid_plan_kernel(const Geo p, const PlanBuf out) {
+  __shared__ int s_key[BM], s_ckey[BM], s_cbase[BM], s_cmask[BM];
+  __shared__ short s_cslot[BM * 4];
+  __shared__ int s_first[NC], s_last[NC], s_scan[8];
+  const unsigned tile = blockIdx.x;
+  const int it = threadIdx.x;
+  uint32_t* const ent = out.ent + (static_cast<size_t>(tile) * BM + it) * kEntPad;
+  unsigned long long* const rows = out.rows + static_cast<size_t>(tile) * kMaxRows;
   TileSpan t;
-  const bool live = tile < p.n_tiles && tile_span(p.tm, tile, t);
-  if (!live) {
-    if (own) {
-#pragma unroll
-      for (int e = 0; e < kEnt; ++e) sm.ent[it * kEnt + e] = kEmpty;
-    }
-    return 0;
+  if (!tile_span(p.tm, tile, t)) {                                // uniform: tile outside [begin, end)
+    if (it == 0) out.hdr[tile] = 0;
+    return;
   }
   const int lane = it & 31, w = it >> 5;
   const int s = it;
@@ -203,8 +216,8 @@ __device__ __noinline__ int plan_list(const Params& p, const PlanSmem& sm, unsig
       key = y0 * S + x0;
     }
   }
-  sm.key[s] = key;
-  // ---- voxel index / weights per (level, class) ----
+  s_key[s] = key;
+  // ---- voxel index / weights per (level, class) (reference modules.py:262-265) ----
   int vi0[NC];
   uint32_t vw[NC];                                                // bf16 w0 | bf16 w1 << 16, i1 == i0 flagged by w1 == 0xffff
 #pragma unroll
@@ -220,31 +233,31 @@ __device__ __noinline__ int plan_list(const Params& p, const PlanSmem& sm, unsig
       const float b = 1.0f - a;
       const uint32_t w0b = bf16_bits(big0 ? a : b), w1b = bf16_bits(big0 ? b : a);
       vw[c] = w0b | ((ax.i1 != ax.i0 ? w1b : 0xffffu) << 16);
-      if (s == t.s_lo) sm.first[c] = ax.i0;
-      if (s == t.s_hi - 1) sm.last[c] = ax.i1;
+      if (s == t.s_lo) s_first[c] = ax.i0;
+      if (s == t.s_hi - 1) s_last[c] = ax.i1;
     }
   }
-  ibar();
+  __syncthreads();
   int vbase[NC + 1];
   vbase[0] = 0;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) vbase[c + 1] = vbase[c] + (c / 3 < p.nh ? sm.last[c] - sm.first[c] + 1 : 0);
+  for (int c = 0; c < NC; ++c) vbase[c + 1] = vbase[c] + (c / 3 < p.nh ? s_last[c] - s_first[c] + 1 : 0);
   const int nvox = vbase[NC];
   // ---- pixel cells: a step opens a new cell when its key differs from the previous step's ----
-  const bool isnew = key >= 0 && (s == 0 || sm.key[s - 1] != key);
+  const bool isnew = key >= 0 && (s == 0 || s_key[s - 1] != key);
   const uint32_t bal = __ballot_sync(0xffffffffu, isnew);
-  if (lane == 0) sm.scan[w] = __popc(bal);
-  ibar();
+  if (lane == 0) s_scan[w] = __popc(bal);
+  __syncthreads();
   int woff = 0;
 #pragma unroll
-  for (int i = 0; i < kIntWarps; ++i) woff += i < w ? sm.scan[i] : 0;
+  for (int i = 0; i < BM / 32; ++i) woff += i < w ? s_scan[i] : 0;
   const int mycell = woff + __popc(bal & ((1u << lane) - 1u)) + (isnew ? 1 : 0) - 1;   // cell of this step (-1: none yet)
-  if (isnew) sm.ckey[mycell] = key;
-  ibar();
+  if (isnew) s_ckey[mycell] = key;
+  __syncthreads();
   // ---- which nodes of a new cell are new (not shared with the previous cell) ----
   int newmask = 0, validmask = 0;
   if (isnew) {
-    const int pk = mycell > 0 ? sm.ckey[mycell - 1] : -1;
+    const int pk = mycell > 0 ? s_ckey[mycell - 1] : -1;
     const int py0 = pk >= 0 ? pk / S : 0, px0 = pk >= 0 ? pk - py0 * S : 0;
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -262,15 +275,14 @@ __device__ __noinline__ int plan_list(const Params& p, const PlanSmem& sm, unsig
     const int u = __shfl_up_sync(0xffffffffu, inc, o);
     if (lane >= o) inc += u;
   }
-  if (lane == 31) sm.scan[4 + w] = inc;
-  ibar();
+  if (lane == 31) s_scan[4 + w] = inc;
+  __syncthreads();
   int wbase = 0, npix = 0;
 #pragma unroll
-  for (int i = 0; i < kIntWarps; ++i) { wbase += i < w ? sm.scan[4 + i] : 0; npix += sm.scan[4 + i]; }
+  for (int i = 0; i < BM / 32; ++i) { wbase += i < w ? s_scan[4 + i] : 0; npix += s_scan[4 + i]; }
   const int base = wbase + inc - cnt;
-  if (isnew) { sm.cbase[mycell] = base; sm.cmask[mycell] = newmask | (validmask << 4); }
-  ibar();
-  uint32_t* const rows = sm.rows + L * kMaxRows;
+  if (isnew) { s_cbase[mycell] = base; s_cmask[mycell] = newmask | (validmask << 4); }
+  __syncthreads();
   if (isnew) {
 #pragma unroll
     for (int n = 0; n < 4; ++n) {
@@ -279,57 +291,64 @@ __device__ __noinline__ int plan_list(const Params& p, const PlanSmem& sm, unsig
         const int nx = x0 + (n & 1), ny = y0 + (n >> 1);
         if ((newmask >> n) & 1) {
           slot = base + __popc(newmask & ((1 << n) - 1));
-          rows[nvox + slot] = kKindPix | static_cast<uint32_t>(ny * S + nx);
+          rows[nvox + slot] = reinterpret_cast<unsigned long long>(p.pmap + static_cast<size_t>(ny * S + nx) * N0);
         } else {
           for (int cc = mycell - 1; cc >= 0; --cc) {              // the node keeps the slot of the cell that introduced it
-            const int ck = sm.ckey[cc];
+            const int ck = s_ckey[cc];
             const int cy0 = ck / S, cx0 = ck - cy0 * S;
             const int which = (nx - cx0) + 2 * (ny - cy0);
-            const int m = sm.cmask[cc];
-            if ((m >> which) & 1) { slot = sm.cbase[cc] + __popc(m & ((1 << which) - 1)); break; }
+            const int m = s_cmask[cc];
+            if ((m >> which) & 1) { slot = s_cbase[cc] + __popc(m & ((1 << which) - 1)); break; }
           }
         }
       }
-      sm.cslot[mycell * 4 + n] = static_cast<short>(slot);
+      s_cslot[mycell * 4 + n] = static_cast<short>(slot);
     }
   }
   // ---- voxel rows: contiguous node ranges of the line table ----
-  const uint32_t line_row0 = t.line_rel * static_cast<uint32_t>(p.rpl);
-  for (int e = it; e < nvox; e += kIntWarps * 32) {
-    int c = 0;
+  const size_t line_row0 = static_cast<size_t>(t.line_rel) * p.rpl;
+  for (int e = it; e < nvox; e += BM) {
+    int c = 0, vb = 0;
 #pragma unroll
     for (int i = 1; i < NC; ++i)
-      if (e >= vbase[i]) c = i;
-    rows[e] = kKindG | (line_row0 + static_cast<uint32_t>(p.rowbase[c / 3] + (c % 3) * p.R[c / 3] + sm.first[c] + (e - vbase[c])));
+      if (e >= vbase[i]) { c = i; vb = vbase[i]; }
+    const int h = c / 3;
+    rows[e] = reinterpret_cast<unsigned long long>(
+        p.G + (line_row0 + static_cast<size_t>(p.rowbase[h] + (c - 3 * h) * p.R[h] + s_first[c] + (e - vb))) * N0);
   }
   const int n_rows = nvox + npix;
   const int n_chunks = (n_rows + BK - 1) / BK;
-  for (int e = n_rows + it; e < n_chunks * BK; e += kIntWarps * 32) rows[e] = kKindZero;
-  ibar();
-  if (own) {
-    uint32_t* const ent = sm.ent + s * kEnt;
+  for (int e = n_rows + it; e < n_chunks * BK; e += BM) rows[e] = reinterpret_cast<unsigned long long>(p.zero);
+  if (it == 0) out.hdr[tile] = n_chunks;
+  __syncthreads();
+  // ---- weight entries of this step: chunk << 23 | byte offset in the row's 128 B (16-byte pieces XOR-swizzled with the
+  //      row index, as the K-major SWIZZLE_128B operand layout wants) << 16 | bf16 weight ----
+  auto entry = [&](int slot, uint32_t wbits) -> uint32_t {
+    const uint32_t col = static_cast<uint32_t>(slot) & 63u;
+    const uint32_t off = (((col >> 3) ^ static_cast<uint32_t>(s & 7)) << 4) | ((col & 7u) << 1);
+    return (static_cast<uint32_t>(slot >> 6) << 23) | (off << 16) | (wbits & 0xffffu);
+  };
+  uint32_t ev[kEntPad];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      uint32_t e0 = kEmpty, e1 = kEmpty;
-      if (c / 3 < p.nh && valid) {
-        const uint32_t slot0 = static_cast<uint32_t>(vbase[c] + vi0[c] - sm.first[c]);
-        e0 = (slot0 << 16) | (vw[c] & 0xffffu);
-        if ((vw[c] >> 16) != 0xffffu) e1 = ((slot0 + 1) << 16) | (vw[c] >> 16);
-      }
-      ent[2 * c] = e0;
-      ent[2 * c + 1] = e1;
-    }
+  for (int e = 0; e < kEntPad; ++e) ev[e] = kEmpty;
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      uint32_t e = kEmpty;
-      if (key >= 0) {
-        const int cs = sm.cslot[mycell * 4 + n];
-        if (cs >= 0) e = (static_cast<uint32_t>(nvox + cs) << 16) | bf16_bits(pw[n]);
-      }
-      ent[2 * NC + n] = e;
+  for (int c = 0; c < NC; ++c) {
+    if (c / 3 < p.nh && valid) {
+      const int slot0 = vbase[c] + vi0[c] - s_first[c];
+      ev[2 * c] = entry(slot0, vw[c] & 0xffffu);
+      if ((vw[c] >> 16) != 0xffffu) ev[2 * c + 1] = entry(slot0 + 1, vw[c] >> 16);
     }
   }
-  return n_chunks;
+  if (key >= 0) {
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      const int cs = s_cslot[mycell * 4 + n];
+      if (cs >= 0) ev[2 * NC + n] = entry(nvox + cs, bf16_bits(pw[n]));
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kEntPad / 4; ++i)
+    reinterpret_cast<uint4*>(ent)[i] = make_uint4(ev[4 * i], ev[4 * i + 1], ev[4 * i + 2], ev[4 * i + 3]);
 }
 
 // ------------------------------------------------------------------ kernel
@@ -345,15 +364,13 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   float* const s_b1 = s_b0 + N0;
   float* const s_b2 = s_b1 + N1;
   float* const s_w3 = s_b2 + N2;
-  int* const s_misc = reinterpret_cast<int*>(gbase + OFF_MISC);
-  volatile int* const s_plan = s_misc + 2 * NC + 8;              // [2][2] chunk counts of the two lists, double buffered
   const uint32_t bar0 = base + OFF_BAR;
   auto full_bar = [&](uint32_t b) { return bar0 + 8u * b; };
   auto empty_bar = [&](uint32_t b) { return bar0 + 8u * (NB + b); };
   auto grant_bar = [&](uint32_t b) { return bar0 + 8u * (2 * NB + b); };
-  const uint32_t dfull_bar = bar0 + 8u * (3 * NB);
+  auto ifull_bar = [&](uint32_t b) { return bar0 + 8u * (3 * NB + b); };
+  const uint32_t dfull_bar = bar0 + 8u * (4 * NB);
   const uint32_t hready_bar = dfull_bar + 8u;
-  auto plan_bar = [&](uint32_t i) { return hready_bar + 8u + 8u * i; };
   const uint32_t tmem_slot = bar0 + 8u * NUM_BARS;
   volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + OFF_BAR + NUM_BARS * 8);
   auto unit_addr = [&](uint32_t u) { return base + (u % NU) * UNIT_BYTES; };
@@ -364,8 +381,10 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int num_clusters = gridDim.x / CG;
   const int n_pairs = static_cast<int>((p.n_tiles + 1) / 2);
   const int nkF = p.nkF;
+  // 64-row interpolation chunks of a tile's row list (grid_plan_kernel); 0 for the tile past the end of an odd launch
+  auto chunks_of = [&](unsigned tile) -> int { return tile < p.n_tiles ? __ldg(p.plan.hdr + tile) : 0; };
 
-  constexpr int kTraceTiles = 16, kTraceSlots = 12;
+  constexpr int kTraceTiles = 16, kTraceSlots = 24;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   auto stamp = [&](int tile_no, int slot) {
     if (tracing && tile_no < kTraceTiles) p.trace[tile_no * kTraceSlots + slot] = clock64();
@@ -377,14 +396,13 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
     for (int b = 0; b < NB; ++b) {
-      mbar_init(full_bar(b), CG);                     // one arrival per CTA (TMA thread or an interp warp)
+      mbar_init(full_bar(b), 1);                      // TMA chunks: the leader's expect_tx covers both CTAs' bytes
       mbar_init(empty_bar(b), 1);
       mbar_init(grant_bar(b), 1);
+      mbar_init(ifull_bar(b), CG);                    // I chunks: one arrival per CTA (the interp warp that filled it)
     }
     mbar_init(dfull_bar, 1);
     mbar_init(hready_bar, 4 * CG);
-    mbar_init(plan_bar(0), 1);
-    mbar_init(plan_bar(1), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<CG>(tmem_slot);
@@ -422,17 +440,22 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         fifo |= static_cast<unsigned long long>(n == U_FI ? 1 : 0) << fifo_n;
         ++fifo_n;
       };
-      // one arrival per CTA on the leader's full barrier; the leader's also announces the bytes of BOTH CTAs
+      // the leader announces the bytes of BOTH CTAs on its full barrier (its only arrival)
       auto announce = [&](uint32_t b, uint32_t bytes_per_cta) {
         if (rank == 0) mbar_expect_tx(full_bar(b), CG * bytes_per_cta);
-        else mbar_arrive_cluster(mapa(full_bar(b), 0));
       };
-      int itn = 0;
-      for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+      int nI = cluster_id < n_pairs ? chunks_of(2u * cluster_id) + chunks_of(2u * cluster_id + 1) : 0;
+      for (int pair = cluster_id; pair < n_pairs; pair += num_clusters) {
         int64_t g0;
         int s_lo, s_hi;
         tile_rows(p.tm, 2u * pair + rank, p.n_tiles, g0, s_lo, s_hi);
         const int row0 = static_cast<int>(g0 - p.tm.begin);   // may be negative / past the end: TMA zero-fills those rows
+        for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {      // units for the interp warps
+          make_room(U_FI);
+          mbar_arrive_local(grant_bar(q % NB));
+        }
+        const int nxt = pair + num_clusters;                      // next tile pair's count, fetched under this tile's loads
+        nI = nxt < n_pairs ? chunks_of(2u * nxt) + chunks_of(2u * nxt + 1) : 0;
         for (int kc = 0; kc < nkF; ++kc, ++q, head += U_FI) {
           make_room(U_FI);
           const uint32_t b = q % NB;
@@ -442,12 +465,6 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_2d<CG>(&tmW0, fb, unit_addr(head + 1 + j), kc * BK, j * 256 + static_cast<int>(rank) * 128);
-        }
-        mbar_wait(plan_bar(itn & 1), (itn >> 1) & 1);
-        const int nI = s_plan[(itn & 1) * 2] + s_plan[(itn & 1) * 2 + 1];
-        for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {      // units for the interp warps
-          make_room(U_FI);
-          mbar_arrive_local(grant_bar(q % NB));
         }
 #pragma unroll 1
         for (int layer = 1; layer <= 2; ++layer) {
@@ -468,19 +485,48 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       constexpr uint32_t idesc = umma_idesc(128 * CG, 128 * CG);
       constexpr uint32_t idesc_mn = idesc | (1u << 16);           // B operand MN-major (rows of P / G are N-contiguous)
       constexpr uint32_t kCols = 128 * CG;
-      uint32_t q = 0, head = 0, hphase = 0, fphase = 0;
-      auto wait_full = [&]() {
+      uint32_t q = 0, head = 0, hphase = 0, fphase = 0, iphase = 0;
+      auto wait_full = [&]() {                                        // TMA chunk
         const uint32_t b = q % NB;
-        mbar_wait_cluster(full_bar(b), (fphase >> b) & 1u);
+        mbar_wait(full_bar(b), (fphase >> b) & 1u);
         fphase ^= 1u << b;
         tc_fence_after();
       };
+      auto wait_ifull = [&]() {                                       // I chunk: filled by the interp warps of both CTAs
+        const uint32_t b = q % NB;
+        mbar_wait_cluster(ifull_bar(b), (iphase >> b) & 1u);
+        iphase ^= 1u << b;
+        tc_fence_after();
+      };
       int itn = 0;
+      unsigned long long n_chunks_i = 0;
+      int nI = cluster_id < n_pairs ? chunks_of(2u * cluster_id) + chunks_of(2u * cluster_id + 1) : 0;
       for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
         if (itn > 0) { mbar_wait(hready_bar, hphase); hphase ^= 1; }   // previous tile's accumulators drained
         tc_fence_after();
         stamp(itn, 0);
-        // ---- fc_0, dense part: D[0,512) = Xr . W0[:, hoisted..]^T ----
+        // ---- fc_0, interpolated part: D[0,512) = Aw . Brows ----
+        n_chunks_i += static_cast<unsigned long long>(nI);
+        uint32_t acc = 0;                                             // the tile's first MMA overwrites the accumulator
+        for (int ci = 0; ci < nI; ++ci, head += U_FI) {
+          wait_ifull();
+          const uint64_t ad = umma_desc_sw128(unit_addr(head));
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)     // 16 k rows = 2048 B further along K
+              umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k,
+                          umma_desc_mn_sw128(unit_addr(head + 1 + j), p.b_lbo, p.b_sbo) + static_cast<uint64_t>((p.b_kadv >> 4) * k),
+                          idesc_mn, acc | static_cast<uint32_t>(k != 0));
+          }
+          acc = 1;
+          umma_commit<CG>(empty_bar(q % NB));
+          ++q;
+        }
+        stamp(itn, 13);
+        const int nxt = pair + num_clusters;
+        nI = nxt < n_pairs ? chunks_of(2u * nxt) + chunks_of(2u * nxt + 1) : 0;
+        // ---- fc_0, dense part: D += Xr . W0[:, hoisted..]^T ----
         for (int kc = 0; kc < nkF; ++kc, head += U_FI) {
           wait_full();
           const uint64_t ad = umma_desc_sw128(unit_addr(head));
@@ -489,25 +535,9 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k, umma_desc_sw128(unit_addr(head + 1 + j)) + 2 * k, idesc,
-                          (kc | k) != 0 ? 1u : 0u);
+                          acc | static_cast<uint32_t>(k != 0));
           }
-          umma_commit<CG>(empty_bar(q % NB));
-          ++q;
-        }
-        // ---- fc_0, interpolated part: D += Aw . Brows ----
-        mbar_wait(plan_bar(itn & 1), (itn >> 1) & 1);
-        const int nI = s_plan[(itn & 1) * 2] + s_plan[(itn & 1) * 2 + 1];
-        for (int ci = 0; ci < nI; ++ci, head += U_FI) {
-          wait_full();
-          const uint64_t ad = umma_desc_sw128(unit_addr(head));
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)     // 16 k rows = 2048 B further along K
-              umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k,
-                          umma_desc_mn_sw128(unit_addr(head + 1 + j), p.b_lbo, p.b_sbo) + static_cast<uint64_t>((p.b_kadv >> 4) * k),
-                          idesc_mn, 1u);
-          }
+          acc = 1;
           umma_commit<CG>(empty_bar(q % NB));
           ++q;
         }
@@ -532,6 +562,10 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           umma_commit<CG>(dfull_bar);
           stamp(itn, 2 * layer + 1);
         }
+      }
+      if (p.stats != nullptr) {
+        atomicAdd(p.stats, static_cast<unsigned long long>(itn));
+        atomicAdd(p.stats + 1, n_chunks_i);
       }
     }
   } else if (warp < kIntWarp0) {
@@ -622,35 +656,37 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else {
     // =========================== interp warps ===========================
-    const int it = threadIdx.x - kIntWarp0 * 32;                   // 0..127 = step of the tile
+    const int it = threadIdx.x - kIntWarp0 * 32;                   // 0..127
     const int wq = it >> 5;
-    PlanSmem sm;
-    sm.ent = reinterpret_cast<uint32_t*>(gbase + OFF_ENT);
-    sm.rows = reinterpret_cast<uint32_t*>(gbase + OFF_ROWS);
-    sm.key = reinterpret_cast<int*>(gbase + OFF_KEY);
-    sm.ckey = reinterpret_cast<int*>(gbase + OFF_CKEY);
-    sm.cbase = reinterpret_cast<int*>(gbase + OFF_CBASE);
-    sm.cmask = reinterpret_cast<int*>(gbase + OFF_CMASK);
-    sm.cslot = reinterpret_cast<short*>(gbase + OFF_CSLOT);
-    sm.first = s_misc;
-    sm.last = s_misc + NC;
-    sm.scan = s_misc + 2 * NC;
-    const uint32_t ent_addr = base + OFF_ENT;
+    const uint32_t ent_addr = base + OFF_ENT, rows_addr = base + OFF_ROWS;
+    uint32_t* const s_ent = reinterpret_cast<uint32_t*>(gbase + OFF_ENT);
+    const unsigned long long* const s_rows = reinterpret_cast<const unsigned long long*>(gbase + OFF_ROWS);
     // this lane's part of a listed row: j = which 256-channel block of N0, g = which 64-channel group of the CTA's 128, c16 = 16-byte piece
     const int bj = lane >> 4, bg = (lane >> 3) & 1, bc = lane & 7;
     const int col_off = bj * 256 + static_cast<int>(rank) * 128 + bg * 64 + bc * 8;
+    auto ibar = [&]() { named_bar_sync(2, kIntWarps * 32); };
     uint32_t q = 0, head = 0, gphase = 0;
     int itn = 0;
     for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+      if (it == 0) stamp(itn, 16);
       ibar();                                                      // every warp is done with the previous tile's lists
-      const int nI0 = plan_list(p, sm, 2u * pair, 0, rank == 0, it);
-      const int nI1 = plan_list(p, sm, 2u * pair + 1, 1, rank == 1, it);
-      if (it == 0) { s_plan[(itn & 1) * 2] = nI0; s_plan[(itn & 1) * 2 + 1] = nI1; }
+      // ---- this tile pair's plan: both row lists, and the entries of this CTA's own tile ----
+      const int nI0 = chunks_of(2u * pair), nI1 = chunks_of(2u * pair + 1);
+      const unsigned own = 2u * pair + rank;
+      if (own < p.n_tiles) {
+        const char* src = reinterpret_cast<const char*>(p.plan.ent + static_cast<size_t>(own) * BM * kEntPad);
+        for (int i = it; i < kPlanEntBytes / 16; i += kIntWarps * 32) cp_async16(ent_addr + 16u * i, src + 16 * i);
+      }
+#pragma unroll
+      for (int L = 0; L < 2; ++L) {
+        const int n16 = (L ? nI1 : nI0) * BK * 8 / 16;
+        const char* src = reinterpret_cast<const char*>(p.plan.rows + static_cast<size_t>(2u * pair + L) * kMaxRows);
+        for (int i = it; i < n16; i += kIntWarps * 32) cp_async16(rows_addr + static_cast<uint32_t>(L * kPlanRowBytes) + 16u * i, src + 16 * i);
+      }
+      cp_async_wait_all();
       ibar();
-      if (it == 0) mbar_arrive_local(plan_bar(itn & 1));
+      if (it == 0) stamp(itn, 14);
       const int nI = nI0 + nI1;
-      q += nkF;
-      head += U_FI * nkF;
       for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {
         const uint32_t b = q % NB;
         const uint32_t par = (gphase >> b) & 1u;
@@ -659,6 +695,7 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int L = ci >= nI0 ? 1 : 0;
         const int c = L ? ci - nI0 : ci;
         mbar_wait_warp(grant_bar(b), par);
+        if (it == 0 && ci == 0) stamp(itn, 19);
         // ---- Aw: zeros, then this CTA's weights if the list is its own tile's ----
         const uint32_t ua = unit_addr(head);
 #pragma unroll 8
@@ -669,40 +706,51 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           for (int rr = 0; rr < BM / 32; ++rr) {
             const int row = rr * 32 + lane;
             const uint32_t ra = ua + static_cast<uint32_t>(row) * 128u;
+            const uint4* const ev = reinterpret_cast<const uint4*>(s_ent + row * kEntPad);
+            uint4 e4[kEntPad / 4];
 #pragma unroll
-            for (int e = 0; e < kEnt; ++e) {
-              uint32_t v;
-              asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(ent_addr + static_cast<uint32_t>(row * kEnt + e) * 4u) : "memory");
-              if (static_cast<int>(v >> 22) == c) {
-                const uint32_t col = (v >> 16) & 63u;
-                st_shared_u16(ra + ((((col >> 3) ^ static_cast<uint32_t>(row & 7))) << 4) + (col & 7u) * 2u, v & 0xffffu);
+            for (int i = 0; i < kEntPad / 4; ++i) e4[i] = ev[i];
+#pragma unroll
+            for (int i = 0; i < kEntPad / 4; ++i) {
+              const uint32_t vv[4] = {e4[i].x, e4[i].y, e4[i].z, e4[i].w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint32_t v = vv[j];
+                if (static_cast<int>(v >> 23) == c) st_shared_u16(ra + ((v >> 16) & 0x7fu), v & 0xffffu);
               }
             }
           }
         }
+        if (it == 0 && ci == 0) stamp(itn, 20);
         // ---- Brows: this CTA's 256 channels of the 64 listed rows, MN-major 128B-swizzled (row k of a 64-channel group
         //      at (k / 8) * 1024 + (k % 8) * 128, 16-byte piece i at (i ^ (k % 8)) * 16; groups 8 KB apart) ----
         const uint32_t ub = unit_addr(head + 1 + bj) + static_cast<uint32_t>(bg) * 8192u;
-        const uint32_t* const lrows = sm.rows + L * kMaxRows + c * BK;
+        const ulonglong2* const lrows = reinterpret_cast<const ulonglong2*>(s_rows + L * kMaxRows + c * BK);
 #pragma unroll 8
-        for (int k = 0; k < BK; ++k) {
-          const uint32_t r = lrows[k];
-          const uint32_t kind = r & ~kIdxMask;
-          const __nv_bfloat16* src = kind == kKindG ? p.G : (kind == kKindPix ? p.pmap : p.zero);
-          src += static_cast<size_t>(kind == kKindZero ? 0u : (r & kIdxMask)) * N0 + col_off;
-          cp_async16(ub + static_cast<uint32_t>(k >> 3) * 1024u + static_cast<uint32_t>(k & 7) * 128u +
-                         (static_cast<uint32_t>(bc ^ (k & 7)) << 4), src);
+        for (int k2 = 0; k2 < BK / 2; ++k2) {
+          const ulonglong2 rr2 = lrows[k2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k = 2 * k2 + u;
+            cp_async16(ub + static_cast<uint32_t>(k >> 3) * 1024u + static_cast<uint32_t>(k & 7) * 128u +
+                           (static_cast<uint32_t>(bc ^ (k & 7)) << 4),
+                       reinterpret_cast<const __nv_bfloat16*>(u ? rr2.y : rr2.x) + col_off);
+          }
         }
+        if (it == 0 && ci == 0) stamp(itn, 21);
         cp_async_wait_all();
+        if (it == 0 && ci == 0) stamp(itn, 22);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (rank == 0) mbar_arrive_local(full_bar(b));
-          else mbar_arrive_cluster(mapa(full_bar(b), 0));
+          if (rank == 0) mbar_arrive_local(ifull_bar(b));
+          else mbar_arrive_cluster(mapa(ifull_bar(b), 0));
         }
+        if (it == 0 && ci == 0) stamp(itn, 23);
       }
-      q += N_W;
-      head = (head + N_W) % NU;
+      if (it == 0) stamp(itn, 15);
+      q += nkF + N_W;
+      head = (head + U_FI * nkF + N_W) % NU;
     }
   }
 
@@ -717,51 +765,80 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
 }  // namespace gtc
 
+static int fill_geo(const ListCtx* ctx, const hoist::Plan& pl, const void* hoist_buf, int image, int res, double bb_min, double bb_max,
+                    int64_t begin, int64_t count, const void* G, gtc::Geo* g) {
+  using namespace gtc;
+  LIST_CHECK_ARG(pl.nh <= kMaxLev, "grid_tc: plan with %d hoisted levels", pl.nh);
+  int vox_rows = 0;
+  for (int h = 0; h < pl.nh; ++h) {
+    LIST_CHECK_ARG(ctx->vol_res[pl.lev[h]] <= 32, "grid_tc: hoisted level with R = %d > 32", ctx->vol_res[pl.lev[h]]);
+    vox_rows += 3 * ctx->vol_res[pl.lev[h]];
+  }
+  LIST_CHECK_ARG(vox_rows + 4 * BM <= kMaxRows, "grid_tc: %d voxel rows per tile exceed the row list", vox_rows);
+  hoist::fill_tilemap(&g->tm, res, bb_min, bb_max, begin, count, BM);
+  g->n_tiles = hoist::tile_count(g->tm);
+  const char* hb = static_cast<const char*>(hoist_buf);
+  g->pmap = reinterpret_cast<const __nv_bfloat16*>(hb + pl.off_pmap) + static_cast<size_t>(image) * ctx->map_size * ctx->map_size * N0;
+  g->G = static_cast<const __nv_bfloat16*>(G);
+  g->zero = reinterpret_cast<const __nv_bfloat16*>(hb + pl.off_zero);
+  g->T = ctx->trans_mat + image * 12;
+  g->S = ctx->map_size;
+  g->nh = pl.nh;
+  g->rpl = pl.rpl;
+  for (int h = 0; h < kMaxLev; ++h) {
+    g->R[h] = h < pl.nh ? ctx->vol_res[pl.lev[h]] : 1;
+    g->rowbase[h] = h < pl.nh ? pl.rowbase[h] : 0;
+  }
+  return LIST_OK;
+}
+
+// Bytes of the tile plans of grid points [begin, begin + count) of a res^3 grid.
+size_t grid_plan_bytes(int res, int64_t begin, int64_t count) {
+  if (count <= 0) return 0;
+  hoist::TileMap tm;
+  hoist::fill_tilemap(&tm, res, 0.0, 1.0, begin, count, gtc::BM);
+  return gtc::plan_bytes(hoist::tile_count(tm));
+}
+
+// Tile plans (row lists + weight entries) of grid points [begin, begin + count) of image `image`; G is only used as an
+// address (the plans point into it), so this may run before or after hoist::lines.
+int grid_plan(const ListCtx* ctx, const hoist::Plan& pl, const void* hoist_buf, int image, int res, double bb_min, double bb_max,
+              int64_t begin, int64_t count, const void* G, void* plan_buf, cudaStream_t st) {
+  using namespace gtc;
+  if (count == 0) return LIST_OK;
+  Geo g{};
+  const int rc = fill_geo(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, G, &g);
+  if (rc) return rc;
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(plan_buf) & 255) == 0, "grid_plan: plan buffer must be 256-byte aligned");
+  grid_plan_kernel<<<g.n_tiles, BM, 0, st>>>(g, plan_carve(plan_buf, g.n_tiles));
+  LIST_LAUNCH_CHECK("grid_plan_kernel");
+  return LIST_OK;
+}
+
 // Fused interpolation + MLP over grid points [begin, begin + count) of image `image` (see the header comment).
-int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, const void* hoist_buf, int image, int res,
-                double bb_min, double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G, float* sdf,
-                float out_div, float* dbg1, long long* trace, cudaStream_t st) {
+int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, int res, double bb_min, double bb_max, int64_t begin,
+                int64_t count, const void* Xr, int64_t ldx, const void* plan_buf, float* sdf, float out_div, float* dbg1,
+                long long* trace, unsigned long long* stats, cudaStream_t st) {
   using namespace gtc;
   if (count == 0) return LIST_OK;
   LIST_CHECK_ARG(w->n0 == N0 && w->n1 == N1 && w->n2 == N2, "grid_tc: layer widths must be 512/256/256 (got %d/%d/%d)", w->n0, w->n1, w->n2);
   LIST_CHECK_ARG(count < (1LL << 31), "grid_tc: %lld rows are too many for one launch", (long long)count);
   const int k_f = pl.k_h - N0;
   LIST_CHECK_ARG(k_f >= BK && k_f % BK == 0 && ldx >= k_f && ldx % 8 == 0, "grid_tc: %d dense columns / ldx %lld invalid", k_f, (long long)ldx);
-  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(Xr) & 15) == 0 && (reinterpret_cast<uintptr_t>(G) & 15) == 0, "grid_tc: Xr / G must be 16-byte aligned");
-  LIST_CHECK_ARG(pl.nh <= kMaxLev && ctx->map_size * ctx->map_size < (1 << 30), "grid_tc: plan not covered");
-  for (int h = 0; h < pl.nh; ++h)
-    LIST_CHECK_ARG(ctx->vol_res[pl.lev[h]] <= 32, "grid_tc: hoisted level with R = %d > 32", ctx->vol_res[pl.lev[h]]);
+  LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(Xr) & 15) == 0 && (reinterpret_cast<uintptr_t>(plan_buf) & 255) == 0,
+                 "grid_tc: Xr must be 16-byte and the plan buffer 256-byte aligned");
   Params p{};
   p.b0 = w->b0; p.b1 = w->b1; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
   p.sdf = sdf;
   p.out_div = out_div;
   p.nkF = k_f / BK;
-  p.x_rows = static_cast<int>(count);
   hoist::fill_tilemap(&p.tm, res, bb_min, bb_max, begin, count, BM);
   p.n_tiles = hoist::tile_count(p.tm);
-  LIST_CHECK_ARG(static_cast<uint64_t>(hoist::line_count(p.tm)) * pl.rpl < (1ull << 30), "grid_tc: line table too large for one launch");
-  const char* hb = static_cast<const char*>(hoist_buf);
-  p.pmap = reinterpret_cast<const __nv_bfloat16*>(hb + pl.off_pmap) + static_cast<size_t>(image) * ctx->map_size * ctx->map_size * N0;
-  p.G = static_cast<const __nv_bfloat16*>(G);
-  p.zero = reinterpret_cast<const __nv_bfloat16*>(hb + pl.off_zero);
-  p.T = ctx->trans_mat + image * 12;
-  p.S = ctx->map_size;
-  p.nh = pl.nh;
-  p.rpl = pl.rpl;
-  for (int h = 0; h < kMaxLev; ++h) {
-    p.R[h] = h < pl.nh ? ctx->vol_res[pl.lev[h]] : 1;
-    p.rowbase[h] = h < pl.nh ? pl.rowbase[h] : 0;
-  }
+  p.plan = plan_carve(const_cast<void*>(plan_buf), p.n_tiles);
   p.dbg1 = dbg1;
   p.trace = trace;
+  p.stats = stats;
   p.b_lbo = 8192; p.b_sbo = 1024; p.b_kadv = 2048;
-  if (const char* e = getenv("LIST_B200_TC_DESC")) {           // bring-up aid: "lbo,sbo,kadv" in bytes
-    unsigned a = 0, b = 0, c = 0;
-    if (sscanf(e, "%u,%u,%u", &a, &b, &c) == 3) { p.b_lbo = a; p.b_sbo = b; p.b_kadv = c; }
-  }
-  int vox_rows = 0;
-  for (int h = 0; h < pl.nh; ++h) vox_rows += 3 * ctx->vol_res[pl.lev[h]];
-  LIST_CHECK_ARG(vox_rows + 4 * BM <= kMaxRows, "grid_tc: %d voxel rows per tile exceed the row list", vox_rows);
   CUtensorMap tmX, tmW0, tmW1, tmW2;
   int rc;
   if ((rc = make_map_bf16(&tmX, Xr, static_cast<uint64_t>(k_f), static_cast<uint64_t>(count), static_cast<uint64_t>(ldx)))) return rc;

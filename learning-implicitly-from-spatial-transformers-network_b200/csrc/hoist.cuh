@@ -35,10 +35,15 @@ int lines(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int re
 
 }  // namespace hoist
 
-// grid_tc.cu: fused interpolation + MLP over the rows of grid points [begin, begin + count): Xr = the non-hoisted columns
-// [count][ldx] (hoist::gather with kPartRest on a pointer shifted by -512 columns), G = hoist::lines of the same range
-int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, const void* hoist_buf, int image, int res,
-                double bb_min, double bb_max, int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* G, float* sdf,
-                float out_div, float* dbg1, long long* trace, cudaStream_t st);
+// grid_tc.cu.  grid_plan: per tile of 128 steps the list of source rows (rows of the projected map and of the line tables G)
+// and the interpolation weights of every step; grid_tc_fwd: fused interpolation + MLP over the rows of grid points
+// [begin, begin + count): Xr = the non-hoisted columns [count][ldx] (hoist::gather with kPartRest on a pointer shifted by
+// -512 columns), plan_buf = grid_plan of the same range (its rows point into G = hoist::lines of the same range).
+size_t grid_plan_bytes(int res, int64_t begin, int64_t count);
+int grid_plan(const ListCtx* ctx, const hoist::Plan& pl, const void* hoist_buf, int image, int res, double bb_min, double bb_max,
+              int64_t begin, int64_t count, const void* G, void* plan_buf, cudaStream_t st);
+int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, int res, double bb_min, double bb_max, int64_t begin,
+                int64_t count, const void* Xr, int64_t ldx, const void* plan_buf, float* sdf, float out_div, float* dbg1,
+                long long* trace, unsigned long long* stats, cudaStream_t st);
 
 }  // namespace list

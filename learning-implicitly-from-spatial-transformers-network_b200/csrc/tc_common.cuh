@@ -38,6 +38,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Upper bound (ns) of the hardware suspension of one try_wait: the thread sleeps until the phase completes or the time is
+// up, instead of returning early and spinning on issue slots the other warps of the SM need.
+constexpr uint32_t kSuspendHint = 0x989680u;
 // Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
 // try_wait suspends the thread in hardware for a time slice, so the loop turns over slowly; the
 // clock is consulted only every 64 failed polls.
@@ -45,10 +48,10 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar), "r"(parity)
+      : "r"(bar), "r"(parity), "r"(kSuspendHint)
       : "memory");
   return ok != 0;
 }

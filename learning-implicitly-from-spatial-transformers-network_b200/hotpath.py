@@ -328,18 +328,33 @@ class LineTableState:
                                               X.stride(0), _stream()), "list_lines_rest")
         return X
 
-    def evaluate(self, image: int, res: int, begin: int, count: int, Xr: torch.Tensor, G: torch.Tensor, out_div: float = 1.0,
-                 bb_min: float = -0.5, bb_max: float = 0.5, debug: bool = False, trace: bool = False):
-        """Fused interpolation + MLP.  Returns sdf (count,) [, relu(fc_0) (count, 512) fp32] [, trace (16, 12) int64]."""
-        sdf = torch.empty(count, device=self.dev, dtype=torch.float32)
-        h1 = torch.zeros(count, 512, device=self.dev, dtype=torch.float32) if debug else None
-        tr = torch.zeros(16, 12, device=self.dev, dtype=torch.int64) if trace else None
+    def plan(self, image: int, res: int, begin: int, count: int, G: torch.Tensor, bb_min: float = -0.5, bb_max: float = 0.5,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Tile plans (row lists pointing into self.buf and G, per-step interpolation weights) as an opaque uint8 buffer."""
+        lib = _C.lib()
+        need = lib.list_grid_plan_bytes(res, begin, count)
+        buf = out if out is not None else torch.empty(need, device=self.dev, dtype=torch.uint8)
         cs, ws = self.ctx.struct(), self.base.struct()
         with torch.cuda.device(self.dev):
-            _C.check(_C.lib().list_grid_tc_fwd(C.byref(cs), C.byref(ws), self.buf.data_ptr(), image, res, bb_min, bb_max, begin, count,
-                                               Xr.data_ptr(), Xr.stride(0), G.data_ptr(), sdf.data_ptr(), float(out_div),
+            _C.check(lib.list_grid_plan(C.byref(cs), C.byref(ws), self.buf.data_ptr(), image, res, bb_min, bb_max, begin, count,
+                                        G.data_ptr(), buf.data_ptr(), buf.numel(), _stream()), "list_grid_plan")
+        return buf
+
+    def evaluate(self, res: int, begin: int, count: int, Xr: torch.Tensor, plan: torch.Tensor, out_div: float = 1.0,
+                 bb_min: float = -0.5, bb_max: float = 0.5, debug: bool = False, trace: bool = False,
+                 stats: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+        """Fused interpolation + MLP.  Returns sdf (count,) [, relu(fc_0) (count, 512) fp32] [, trace (16, 24) int64].
+        stats: optional device int64[2] accumulating (tile pairs, interpolation chunks).  The G tensor the plan was built
+        for must still be alive."""
+        sdf = out if out is not None else torch.empty(count, device=self.dev, dtype=torch.float32)
+        h1 = torch.zeros(count, 512, device=self.dev, dtype=torch.float32) if debug else None
+        tr = torch.zeros(16, 24, device=self.dev, dtype=torch.int64) if trace else None
+        cs, ws = self.ctx.struct(), self.base.struct()
+        with torch.cuda.device(self.dev):
+            _C.check(_C.lib().list_grid_tc_fwd(C.byref(cs), C.byref(ws), res, bb_min, bb_max, begin, count,
+                                               Xr.data_ptr(), Xr.stride(0), plan.data_ptr(), sdf.data_ptr(), float(out_div),
                                                None if h1 is None else h1.data_ptr(), None if tr is None else tr.data_ptr(),
-                                               _stream()), "list_grid_tc_fwd")
+                                               None if stats is None else stats.data_ptr(), _stream()), "list_grid_tc_fwd")
         out = [sdf]
         if debug:
             out.append(h1)

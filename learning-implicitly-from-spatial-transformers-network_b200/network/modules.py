@@ -11,7 +11,10 @@ re-stated only so that `LIST` exists with the reference's attribute names and st
 from __future__ import annotations
 
 import math
-from typing import List, Sequence
+import os
+import warnings
+import weakref
+from typing import List, Optional, Sequence
 
 import torch
 import torch.nn as nn
@@ -23,6 +26,28 @@ DISPLACEMENT = 0.0722     # reference modules.py:205
 
 
 # =============================================================================== hot path
+def _inference_only(name: str, *tensors) -> None:
+    """The stand-alone hot modules run the kernels on detached tensors.  Under autograd that would silently train
+    nothing (reference call pattern models.py:93-97), so it is an error: training goes through `LIST.forward`, where
+    gather + MLP are ONE autograd node (hotpath.query_sdf_autograd)."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError(
+            f"list_b200 {name}.forward is inference-only (its inputs require grad): call it under torch.no_grad(), or "
+            "train through list_b200.network.models.LIST.forward, whose hot path is differentiable")
+
+
+def _cached(cache: dict, tensors, build):
+    """`build()` once per set of input tensor OBJECTS (weak references + version counters: a new tensor that happens to
+    reuse the storage address of a freed one never hits), per device."""
+    slot = str(tensors[0].device)
+    hit = cache.get(slot)
+    if hit is not None and len(hit[0]) == len(tensors) and all(r() is t and v == t._version for (r, v), t in zip(hit[0], tensors)):
+        return hit[1]
+    value = build()
+    cache[slot] = ([(weakref.ref(t), t._version) for t in tensors], value)
+    return value
+
+
 class PerceptualPooling(nn.Module):
     """forward(img_featuremaps: 5 x (B,C_i,H_i,W_i), pc: (B,N,3), trans_mat: (B,4,3)) -> (B, sum C_i, 1, N)
 
@@ -35,11 +60,15 @@ class PerceptualPooling(nn.Module):
     def __init__(self, map_size: int = 137):
         super().__init__()
         self.map_size = map_size
+        self._ctx_cache = {}
 
     def forward(self, img_featuremaps: Sequence[torch.Tensor], pc: torch.Tensor, trans_mat: torch.Tensor) -> torch.Tensor:
+        _inference_only("PerceptualPooling", *img_featuremaps, pc, trans_mat)
         B, N, _ = pc.shape
-        dummy = torch.zeros(B, 8, 1, 1, 1, device=pc.device)          # one inert 8-channel level
-        ctx = hotpath.prepare_context(img_featuremaps, [dummy], trans_mat, "fp32", self.map_size)
+        # the reference re-runs the 137^2 upsample of all five maps for every 65 536-point chunk (modules.py:25-35 inside
+        # executors.py:215-224); here the prepared context is kept while the caller passes the same tensors again
+        ctx = _cached(self._ctx_cache, (*img_featuremaps, trans_mat), lambda: hotpath.prepare_context(
+            img_featuremaps, [torch.zeros(B, 8, 1, 1, 1, device=pc.device)], trans_mat, "fp32", self.map_size))
         X = hotpath.gather_features(ctx, pc, raw=False)
         lay = ctx.layout
         cm = ctx.maps_cl.shape[-1]
@@ -80,26 +109,33 @@ class VoxelDecoder2(nn.Module):
         # reference it is NOT moved with .cuda() at construction, so the module builds on CPU hosts
         self.displacments = torch.tensor(rows)
         self._cache = {}
+        self._ctx_cache = {}
 
     # ---- derived kernel weights -------------------------------------------------------------
     def param_dict(self, prefix: str = "fc.") -> dict:
         return {f"{prefix}{k}.{n}": getattr(m, n) for k, m in self.fc.items() for n in ("weight", "bias")}
 
     def kernel_weights(self, layout, dtype="fp32") -> "hotpath.KernelWeights":
+        """Kernel-format copies of the parameters, rebuilt when a parameter changes (version counter / storage).  The cache
+        is keyed per (device, dtype) and the LOCALLY built object is returned: nn.DataParallel replicas share this dict
+        (shallow __dict__ copy, reference train.py:126) and call from parallel threads, one device each."""
         params = self.param_dict()
-        key = (hotpath.dtype_code(dtype), layout.k_pad, tuple(layout.perm[:8]),
-               tuple((p.data_ptr(), p._version) for p in params.values()))
-        hit = self._cache.get("kw")
-        if hit is None or hit[0] != key:
-            self._cache["kw"] = (key, hotpath.prepare_weights(params, layout, dtype))
-        return self._cache["kw"][1]
+        dev = next(iter(params.values())).device
+        slot = (str(dev), hotpath.dtype_code(dtype))
+        key = (layout.k_pad, tuple(layout.perm[:8]), tuple((p.data_ptr(), p._version) for p in params.values()))
+        hit = self._cache.get(slot)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        kw = hotpath.prepare_weights(params, layout, dtype)
+        self._cache[slot] = (key, kw)
+        return kw
 
     def forward(self, p: torch.Tensor, feat: Sequence[torch.Tensor], percep_feat: torch.Tensor) -> torch.Tensor:
+        _inference_only("VoxelDecoder2", p, percep_feat, *feat, *self.parameters())
         B, N, _ = p.shape
         cm = percep_feat.shape[1]
-        inert_map = [torch.zeros(B, cm, 2, 2, device=p.device)]
-        ident = torch.zeros(B, 4, 3, device=p.device)
-        ctx = hotpath.prepare_context(inert_map, feat, ident, "fp32", 2)
+        ctx = _cached(self._ctx_cache, tuple(feat), lambda: hotpath.prepare_context(
+            [torch.zeros(B, cm, 2, 2, device=p.device)], feat, torch.zeros(B, 4, 3, device=p.device), "fp32", 2))
         X = hotpath.gather_features(ctx, p, raw=False)
         lay = ctx.layout
         X[:, lay.map_off:lay.map_off + cm] = percep_feat.detach().permute(0, 2, 1).reshape(B * N, cm)
@@ -185,16 +221,26 @@ class TreeGraphDecoder(nn.Module):
 
 class ResEncoder(nn.Module):
     """ResNet-18 with a stride-1 stem -> (128-d code, 5 feature maps) (modules.py:1027-1074).
-    The reference asks torchvision for pretrained weights (needs network); random init here unless
-    `pretrained=True` is passed and the weights are available locally."""
+    Like the reference (`models.resnet18(pretrained=True)`, modules.py:1030) the backbone starts from the ImageNet weights
+    when torchvision has them in its local cache; without them (this image has no network) it warns once and starts from
+    random init -- loading a LIST checkpoint overwrites every backbone tensor either way.  `pretrained=False` skips the
+    lookup."""
+    _warned = False
 
-    def __init__(self, pretrained: bool = False):
+    def __init__(self, pretrained: Optional[bool] = None):
         super().__init__()
         from torchvision import models
-        try:
-            net = models.resnet18(weights=models.ResNet18_Weights.DEFAULT if pretrained else None)
-        except Exception:                       # offline: fall back to random init
-            net = models.resnet18(weights=None)
+        weights = None
+        if pretrained is None or pretrained:
+            w = models.ResNet18_Weights.DEFAULT
+            cached = os.path.join(torch.hub.get_dir(), "checkpoints", os.path.basename(w.url))
+            if os.path.exists(cached):
+                weights = w
+            elif not ResEncoder._warned:
+                ResEncoder._warned = True
+                warnings.warn(f"ResEncoder: ImageNet weights not found at {cached}; starting from random init "
+                              "(the reference starts from torchvision's pretrained resnet18)")
+        net = models.resnet18(weights=weights)
         self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=1, padding=3, bias=False)
         self.bn1, self.relu, self.maxpool = net.bn1, net.relu, net.maxpool
         self.layer1, self.layer2, self.layer3, self.layer4 = net.layer1, net.layer2, net.layer3, net.layer4

@@ -85,7 +85,8 @@ def run_case(name, res, begin, count, trans, dev, size="full"):
     dX = (Xr.float() - Xfull[:, ls.hoist_cols:ls.hoist_cols + ls.k_f].float()).abs().max().item()
     print(f"Xr vs the full gather's columns [{ls.hoist_cols}, +{ls.k_f}): max|d| {dX:.3e} (expected 0)")
 
-    sdf, h1, tr = ls.evaluate(0, res, begin, count, Xr, G, 1.0, debug=True, trace=True)
+    plan = ls.plan(0, res, begin, count, G)
+    sdf, h1, tr = ls.evaluate(res, begin, count, Xr, plan, 1.0, debug=True, trace=True)
     torch.cuda.synchronize()
     h1_ref = torch.relu(Xfull.float() @ kw.w0.float().t() + kw.b0)
     dh = (h1 - h1_ref).abs()

@@ -180,29 +180,9 @@ def test_grid_kernel_vs_explicit_points_and_shards_compose(mode, res, monkeypatc
         parts.append(hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=777))
     assert torch.equal(torch.cat(parts, dim=1), whole)
     monkeypatch.setenv("LIST_B200_GRID_GENERIC", "1")       # per-point kernel in grid mode ...
-    monkeypatch.setenv("LIST_B200_NO_FUSED", "1")           # ... through the chunked gather + MLP path
     monkeypatch.setenv("LIST_B200_HOIST", "0")              # ... on full (un-hoisted) feature rows
     generic = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=3000)
     assert torch.equal(generic, explicit)
-
-
-def test_fused_grid_kernel_equals_chunked_gather_plus_mlp(monkeypatch):
-    """bf16: the fused gather->MLP kernel (feature rows stay in shared memory) against the chunked
-    gather_grid + mlp_tc kernels: same gather arithmetic, same MMA order."""
-    inp = synth.make_inputs(seed=13, B=2, N=8, size="small", trans="camera")
-    g = inp.to(DEV)
-    ctx, kw = ctx_and_weights(g, "bf16")
-    monkeypatch.setenv("LIST_B200_HOIST", "0")              # both sides on full (un-hoisted) feature rows
-    for res, begin, count in ((24, 0, 24 ** 3), (40, 12345, 20000), (16, 7, 300), (9, 0, 729)):
-        monkeypatch.delenv("LIST_B200_NO_FUSED", raising=False)
-        monkeypatch.setenv("LIST_B200_FUSED", "1")
-        fused = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0)
-        monkeypatch.setenv("LIST_B200_NO_FUSED", "1")
-        chunked = hotpath.grid_sdf(ctx, kw, res, begin, count, sdf_scale=10.0, chunk_rows=4096)
-        err = (fused - chunked).abs().max().item()
-        print(f"fused vs chunked res={res} count={count}: max diff {err:.3e}, bit-exact={torch.equal(fused, chunked)}")
-        assert torch.isfinite(fused).all()
-        assert err <= 1e-5
 
 
 def test_grid_walker_rows_match_generic_rows():
