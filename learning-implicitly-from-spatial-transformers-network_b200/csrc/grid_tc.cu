@@ -23,8 +23,11 @@
 //                CTA copies ITS half of the 512 channels of every listed row (B operand split along N).
 //   Ring       : 12 units of 16 KB, allocated first-in first-out by the TMA thread in consumption order
 //                  I chunk [Aw | Brows j=0 | Brows j=1] -> F chunk [X box | W0 box | W0 box] -> 8 + 4 weight boxes of fc_1 / fc_2.
-//                I chunks are filled by the interp warps once the allocator has granted their units (grant barriers); they
-//                come first in a tile's sequence so that they are granted and filled during the previous tile's fc_1 / fc_2.
+//                I chunks are filled by the interp warps once the allocator has granted their units (grant barriers).  The
+//                first two of each tile of the pair come first in the sequence, so that they are granted and filled during
+//                the previous pair's fc_1 / fc_2 (the ring holds four such chunks); the others follow the F chunks and are
+//                filled under them.  A tile's own chunks thus always sit at the same places relative to its F chunks,
+//                whichever CTA of a pair evaluates it and whatever its partner needs (accumulation order is fixed).
 //   Tile plans : grid_plan_kernel (one CTA per tile, launched before this kernel) writes per tile the list of source rows
 //                (absolute addresses; voxel rows = contiguous node ranges of the line table per (level, class); pixel rows
 //                = the nodes of the pixel cells the tile's path crosses, de-duplicated between consecutive cells) and per
@@ -50,6 +53,7 @@ constexpr int UNIT_BYTES = 128 * BK * 2;           // 16 KB
 constexpr int NU = 12, NB = 12;                    // ring units / chunk barriers
 constexpr int U_FI = 3;                            // units of an F or I chunk
 constexpr int N_W = (N0 + N1) / BK;                // fc_1 + fc_2 weight chunks per tile, one unit each
+constexpr int kIFirst = 2;                         // I chunks of EACH tile of a pair that precede the F chunks in the ring order (the rest follow them)
 constexpr int kEpiWarp0 = 2, kIntWarp0 = 6, kIntWarps = 4;
 constexpr int kThreads = (kIntWarp0 + kIntWarps) * 32;   // 320
 constexpr int kMaxLev = hoist::kMaxLev;
@@ -153,29 +157,11 @@ __device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
 __device__ __forceinline__ void st_shared_u16(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(static_cast<unsigned short>(v)) : "memory");
 }
-// acquire at cluster scope: the barrier was (also) arrived on by the peer CTA, whose shared memory the MMA will read
-__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity), "r"(kSuspendHint)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  if (mbar_try_cluster(bar, parity)) return;
-  long long t0 = 0;
-  uint32_t polls = 0;
-  while (!mbar_try_cluster(bar, parity)) {
-    if ((++polls & 63u) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 8000000000LL) mbar_timeout(bar, parity);
-    }
-  }
+// Remote arrive in the form CUTLASS uses for its cross-CTA pipeline barriers (default semantics).  The data hand-offs it
+// signals are ordered by the proxy / tcgen05 fences executed before it; the explicit .release.cluster form compiles to
+// MEMBAR.ALL.GPU, ~1k cycles on every hand-off.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ uint32_t bf16_bits(float x) { return static_cast<uint32_t>(__bfloat16_as_ushort(__float2bfloat16_rn(x))); }
 
@@ -195,9 +181,14 @@ __global__ void __launch_bounds__(BM) grid_plan_kernel(const Geo p, const PlanBu
     if (it == 0) out.hdr[tile] = 0;
     return;
   }
+  // The plan covers ALL steps of the tile that lie on its z-line, also those outside [begin, end): row list, slot order and
+  // with them the order in which the tensor cores accumulate are then a function of the absolute tile only, which keeps any
+  // chunking / sharding of the grid bit-identical (the steps outside the range are computed and not stored).
+  t.s_lo = 0;
+  t.s_hi = min(p.tm.kPz, p.tm.res - t.gz0);
   const int lane = it & 31, w = it >> 5;
   const int s = it;
-  const bool valid = s >= t.s_lo && s < t.s_hi;
+  const bool valid = s < t.s_hi;
   const int S = p.S;
   const float q0 = valid ? step_q0(p.tm, t, s) : 0.f;
   // ---- pixel cell and bilinear weights (reference modules.py:37-52) ----
@@ -383,6 +374,13 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int nkF = p.nkF;
   // 64-row interpolation chunks of a tile's row list (grid_plan_kernel); 0 for the tile past the end of an odd launch
   auto chunks_of = [&](unsigned tile) -> int { return tile < p.n_tiles ? __ldg(p.plan.hdr + tile) : 0; };
+  // I chunks of a pair as (before the F chunks) | (after them) << 16
+  auto counts_of = [&](int pair) -> int {
+    if (pair >= n_pairs) return 0;
+    const int n0 = chunks_of(2u * pair), n1 = chunks_of(2u * pair + 1);
+    const int a = min(n0, kIFirst) + min(n1, kIFirst);
+    return a | ((n0 + n1 - a) << 16);
+  };
 
   constexpr int kTraceTiles = 16, kTraceSlots = 24;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
@@ -444,18 +442,17 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       auto announce = [&](uint32_t b, uint32_t bytes_per_cta) {
         if (rank == 0) mbar_expect_tx(full_bar(b), CG * bytes_per_cta);
       };
-      int nI = cluster_id < n_pairs ? chunks_of(2u * cluster_id) + chunks_of(2u * cluster_id + 1) : 0;
+      int cnt = counts_of(cluster_id);
       for (int pair = cluster_id; pair < n_pairs; pair += num_clusters) {
         int64_t g0;
         int s_lo, s_hi;
         tile_rows(p.tm, 2u * pair + rank, p.n_tiles, g0, s_lo, s_hi);
         const int row0 = static_cast<int>(g0 - p.tm.begin);   // may be negative / past the end: TMA zero-fills those rows
-        for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {      // units for the interp warps
+        const int nIa = cnt & 0xffff, nIb = cnt >> 16;
+        for (int ci = 0; ci < nIa; ++ci, ++q, head += U_FI) {     // units for the interp warps
           make_room(U_FI);
           mbar_arrive_local(grant_bar(q % NB));
         }
-        const int nxt = pair + num_clusters;                      // next tile pair's count, fetched under this tile's loads
-        nI = nxt < n_pairs ? chunks_of(2u * nxt) + chunks_of(2u * nxt + 1) : 0;
         for (int kc = 0; kc < nkF; ++kc, ++q, head += U_FI) {
           make_room(U_FI);
           const uint32_t b = q % NB;
@@ -466,6 +463,11 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           for (int j = 0; j < 2; ++j)
             tma_load_2d<CG>(&tmW0, fb, unit_addr(head + 1 + j), kc * BK, j * 256 + static_cast<int>(rank) * 128);
         }
+        for (int ci = 0; ci < nIb; ++ci, ++q, head += U_FI) {
+          make_room(U_FI);
+          mbar_arrive_local(grant_bar(q % NB));
+        }
+        cnt = counts_of(pair + num_clusters);                     // next tile pair's counts, fetched under this tile's loads
 #pragma unroll 1
         for (int layer = 1; layer <= 2; ++layer) {
           const CUtensorMap* tm = (layer == 1) ? &tmW1 : &tmW2;
@@ -494,39 +496,40 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       };
       auto wait_ifull = [&]() {                                       // I chunk: filled by the interp warps of both CTAs
         const uint32_t b = q % NB;
-        mbar_wait_cluster(ifull_bar(b), (iphase >> b) & 1u);
+        mbar_wait(ifull_bar(b), (iphase >> b) & 1u);
         iphase ^= 1u << b;
         tc_fence_after();
       };
       int itn = 0;
       unsigned long long n_chunks_i = 0;
-      int nI = cluster_id < n_pairs ? chunks_of(2u * cluster_id) + chunks_of(2u * cluster_id + 1) : 0;
+      int cnt = counts_of(cluster_id);
       for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
         if (itn > 0) { mbar_wait(hready_bar, hphase); hphase ^= 1; }   // previous tile's accumulators drained
         tc_fence_after();
         stamp(itn, 0);
-        // ---- fc_0, interpolated part: D[0,512) = Aw . Brows ----
-        n_chunks_i += static_cast<unsigned long long>(nI);
+        // ---- fc_0: D[0,512) = Aw . Brows (interpolated part, I chunks) + Xr . W0[:, hoisted..]^T (dense part, F chunks) ----
+        const int nIa = cnt & 0xffff, nIb = cnt >> 16;
+        n_chunks_i += static_cast<unsigned long long>(nIa + nIb);
         uint32_t acc = 0;                                             // the tile's first MMA overwrites the accumulator
-        for (int ci = 0; ci < nI; ++ci, head += U_FI) {
-          wait_ifull();
-          const uint64_t ad = umma_desc_sw128(unit_addr(head));
+        auto issue_i = [&](int n) {
+          for (int ci = 0; ci < n; ++ci, head += U_FI) {
+            wait_ifull();
+            const uint64_t ad = umma_desc_sw128(unit_addr(head));
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
+            for (int k = 0; k < BK / 16; ++k) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)     // 16 k rows = 2048 B further along K
-              umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k,
-                          umma_desc_mn_sw128(unit_addr(head + 1 + j), p.b_lbo, p.b_sbo) + static_cast<uint64_t>((p.b_kadv >> 4) * k),
-                          idesc_mn, acc | static_cast<uint32_t>(k != 0));
+              for (int j = 0; j < 2; ++j)     // 16 k rows = 2048 B further along K
+                umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k,
+                            umma_desc_mn_sw128(unit_addr(head + 1 + j), p.b_lbo, p.b_sbo) + static_cast<uint64_t>((p.b_kadv >> 4) * k),
+                            idesc_mn, acc | static_cast<uint32_t>(k != 0));
+            }
+            acc = 1;
+            umma_commit<CG>(empty_bar(q % NB));
+            ++q;
           }
-          acc = 1;
-          umma_commit<CG>(empty_bar(q % NB));
-          ++q;
-        }
+        };
+        issue_i(nIa);
         stamp(itn, 13);
-        const int nxt = pair + num_clusters;
-        nI = nxt < n_pairs ? chunks_of(2u * nxt) + chunks_of(2u * nxt + 1) : 0;
-        // ---- fc_0, dense part: D += Xr . W0[:, hoisted..]^T ----
         for (int kc = 0; kc < nkF; ++kc, head += U_FI) {
           wait_full();
           const uint64_t ad = umma_desc_sw128(unit_addr(head));
@@ -541,6 +544,9 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           umma_commit<CG>(empty_bar(q % NB));
           ++q;
         }
+        stamp(itn, 12);
+        issue_i(nIb);
+        cnt = counts_of(pair + num_clusters);
         umma_commit<CG>(dfull_bar);
         stamp(itn, 1);
         // ---- fc_1: D[256,512) = H1(TMEM [0,256)) . W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) . W2^T ----
@@ -577,7 +583,7 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int r_in_tile = quarter * 32 + lane;
     auto arrive_hready = [&]() {
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(hready_remote);
+      if (lane == 0) mbar_arrive_remote(hready_remote);
     };
     uint32_t dphase = 0;
     int itn = 0;
@@ -687,51 +693,55 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ibar();
       if (it == 0) stamp(itn, 14);
       const int nI = nI0 + nI1;
+      const int a0 = min(nI0, kIFirst), a1 = min(nI1, kIFirst), nIa = a0 + a1;
       for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {
+        if (ci == nIa) { q += nkF; head += U_FI * nkF; }           // the pair's F chunks sit between its two groups of I chunks
         const uint32_t b = q % NB;
         const uint32_t par = (gphase >> b) & 1u;
         gphase ^= 1u << b;
-        if ((ci & (kIntWarps - 1)) != wq) continue;                // chunk ci belongs to warp ci % 4
-        const int L = ci >= nI0 ? 1 : 0;
-        const int c = L ? ci - nI0 : ci;
+        // sequence: list 0 chunks [0, a0), list 1 chunks [0, a1) | F | list 0 chunks [a0, nI0), list 1 chunks [a1, nI1)
+        int L, c;
+        if (ci < a0) { L = 0; c = ci; }
+        else if (ci < nIa) { L = 1; c = ci - a0; }
+        else if (ci < nIa + (nI0 - a0)) { L = 0; c = ci - nIa + a0; }
+        else { L = 1; c = ci - nIa - (nI0 - a0) + a1; }
         mbar_wait_warp(grant_bar(b), par);
         if (it == 0 && ci == 0) stamp(itn, 19);
-        // ---- Aw: zeros, then this CTA's weights if the list is its own tile's ----
-        const uint32_t ua = unit_addr(head);
-#pragma unroll 8
-        for (int i = 0; i < UNIT_BYTES / 16 / 32; ++i) st_shared_zero16(ua + static_cast<uint32_t>(i * 32 + lane) * 16u);
+        // Every chunk is filled by all four warps, a quarter of its rows each: what matters is the latency from the grant
+        // to the chunk being usable, not the throughput.
+        // ---- Aw rows [32 wq, +32): zeros, then this CTA's weights if the list is its own tile's ----
+        const uint32_t ua = unit_addr(head) + static_cast<uint32_t>(wq) * (32u * 128u);
+#pragma unroll
+        for (int i = 0; i < 32 * 128 / 16 / 32; ++i) st_shared_zero16(ua + static_cast<uint32_t>(i * 32 + lane) * 16u);
         __syncwarp();
         if (L == static_cast<int>(rank)) {
-#pragma unroll 1
-          for (int rr = 0; rr < BM / 32; ++rr) {
-            const int row = rr * 32 + lane;
-            const uint32_t ra = ua + static_cast<uint32_t>(row) * 128u;
-            const uint4* const ev = reinterpret_cast<const uint4*>(s_ent + row * kEntPad);
-            uint4 e4[kEntPad / 4];
+          const int row = wq * 32 + lane;
+          const uint32_t ra = ua + static_cast<uint32_t>(lane) * 128u;
+          const uint4* const ev = reinterpret_cast<const uint4*>(s_ent + row * kEntPad);
+          uint4 e4[kEntPad / 4];
 #pragma unroll
-            for (int i = 0; i < kEntPad / 4; ++i) e4[i] = ev[i];
+          for (int i = 0; i < kEntPad / 4; ++i) e4[i] = ev[i];
 #pragma unroll
-            for (int i = 0; i < kEntPad / 4; ++i) {
-              const uint32_t vv[4] = {e4[i].x, e4[i].y, e4[i].z, e4[i].w};
+          for (int i = 0; i < kEntPad / 4; ++i) {
+            const uint32_t vv[4] = {e4[i].x, e4[i].y, e4[i].z, e4[i].w};
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint32_t v = vv[j];
-                if (static_cast<int>(v >> 23) == c) st_shared_u16(ra + ((v >> 16) & 0x7fu), v & 0xffffu);
-              }
+            for (int j = 0; j < 4; ++j) {
+              const uint32_t v = vv[j];
+              if (static_cast<int>(v >> 23) == c) st_shared_u16(ra + ((v >> 16) & 0x7fu), v & 0xffffu);
             }
           }
         }
         if (it == 0 && ci == 0) stamp(itn, 20);
-        // ---- Brows: this CTA's 256 channels of the 64 listed rows, MN-major 128B-swizzled (row k of a 64-channel group
-        //      at (k / 8) * 1024 + (k % 8) * 128, 16-byte piece i at (i ^ (k % 8)) * 16; groups 8 KB apart) ----
-        const uint32_t ub = unit_addr(head + 1 + bj) + static_cast<uint32_t>(bg) * 8192u;
-        const ulonglong2* const lrows = reinterpret_cast<const ulonglong2*>(s_rows + L * kMaxRows + c * BK);
-#pragma unroll 8
-        for (int k2 = 0; k2 < BK / 2; ++k2) {
+        // ---- Brows k in [16 wq, +16): this CTA's 256 channels of the listed rows, MN-major 128B-swizzled (row k of a
+        //      64-channel group at (k / 8) * 1024 + (k % 8) * 128, 16-byte piece i at (i ^ (k % 8)) * 16; groups 8 KB apart) ----
+        const uint32_t ub = unit_addr(head + 1 + bj) + static_cast<uint32_t>(bg) * 8192u + static_cast<uint32_t>(wq) * 2048u;
+        const ulonglong2* const lrows = reinterpret_cast<const ulonglong2*>(s_rows + L * kMaxRows + c * BK + wq * 16);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
           const ulonglong2 rr2 = lrows[k2];
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
-            const int k = 2 * k2 + u;
+            const int k = 2 * k2 + u;                              // row 16 wq + k of the chunk: (k >> 3) is the 8-row group inside this quarter
             cp_async16(ub + static_cast<uint32_t>(k >> 3) * 1024u + static_cast<uint32_t>(k & 7) * 128u +
                            (static_cast<uint32_t>(bc ^ (k & 7)) << 4),
                        reinterpret_cast<const __nv_bfloat16*>(u ? rr2.y : rr2.x) + col_off);
@@ -741,16 +751,17 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         cp_async_wait_all();
         if (it == 0 && ci == 0) stamp(itn, 22);
         fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
+        ibar();                                                    // all four quarters are in place
+        if (it == 0) {
           if (rank == 0) mbar_arrive_local(ifull_bar(b));
-          else mbar_arrive_cluster(mapa(ifull_bar(b), 0));
+          else mbar_arrive_remote(mapa(ifull_bar(b), 0));
         }
         if (it == 0 && ci == 0) stamp(itn, 23);
       }
+      if (nI <= nIa) { q += nkF; head += U_FI * nkF; }
       if (it == 0) stamp(itn, 15);
-      q += nkF + N_W;
-      head = (head + U_FI * nkF + N_W) % NU;
+      q += N_W;
+      head = (head + N_W) % NU;
     }
   }
 
