@@ -17,7 +17,8 @@
 // block of round 1 (34 GB through HBM per 256^3 grid) no longer exists.
 //
 //   Warp roles : warp 0 = TMA producer and ring allocator, warp 1 = TMEM allocator + MMA issuer (one thread),
-//                warps 2..5 = epilogue (one TMEM lane quarter each), warps 6..9 = interp warps (Aw, Brows).
+//                warps 2..9 = epilogue (two per TMEM lane quarter, half of the columns each), warps 10..13 = interp warps
+//                (Aw, Brows).
 //   CG = 2     : CTA pair, tcgen05.mma.cta_group::2, M = 256.  CTA r evaluates tile 2p + r; the K space of the pair's
 //                I chunks is the concatenation of both tiles' row lists (the other CTA's rows get zero weights), and each
 //                CTA copies ITS half of the 512 channels of every listed row (B operand split along N).
@@ -54,8 +55,8 @@ constexpr int NU = 12, NB = 12;                    // ring units / chunk barrier
 constexpr int U_FI = 3;                            // units of an F or I chunk
 constexpr int N_W = (N0 + N1) / BK;                // fc_1 + fc_2 weight chunks per tile, one unit each
 constexpr int kIFirst = 2;                         // I chunks of EACH tile of a pair that precede the F chunks in the ring order (the rest follow them)
-constexpr int kEpiWarp0 = 2, kIntWarp0 = 6, kIntWarps = 4;
-constexpr int kThreads = (kIntWarp0 + kIntWarps) * 32;   // 320
+constexpr int kEpiWarp0 = 2, kEpiWarps = 8, kIntWarp0 = kEpiWarp0 + kEpiWarps, kIntWarps = 4;
+constexpr int kThreads = (kIntWarp0 + kIntWarps) * 32;   // 448
 constexpr int kMaxLev = hoist::kMaxLev;
 constexpr int NC = kMaxLev * 3;                    // (level, W-shift class) combinations
 constexpr int kEnt = 2 * NC + 4;                   // weight entries of a step: two per combination + 4 pixel taps
@@ -91,7 +92,8 @@ constexpr int OFF_PAR = NU * UNIT_BYTES;                           // b0 b1 b2 w
 constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;
 constexpr int OFF_ENT = OFF_PAR + PARAM_FLOATS * 4;                // this CTA's tile: uint32 [128][kEntPad]
 constexpr int OFF_ROWS = OFF_ENT + kPlanEntBytes;                  // uint64 [2][kMaxRows]: both tiles' row lists
-constexpr int OFF_BAR = OFF_ROWS + 2 * kPlanRowBytes;
+constexpr int OFF_PART = OFF_ROWS + 2 * kPlanRowBytes;               // float [128]: fc_out partial sums of the upper column halves
+constexpr int OFF_BAR = OFF_PART + BM * 4;
 constexpr int NUM_BARS = 4 * NB + 2;                               // full empty grant ifull | dfull hready
 constexpr int SMEM_BYTES = OFF_BAR + NUM_BARS * 8 + 16 + 1024 /*align slack*/;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -400,12 +402,12 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_init(ifull_bar(b), CG);                    // I chunks: one arrival per CTA (the interp warp that filled it)
     }
     mbar_init(dfull_bar, 1);
-    mbar_init(hready_bar, 4 * CG);
+    mbar_init(hready_bar, kEpiWarps * CG);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc<CG>(tmem_slot);
   if (warp >= kEpiWarp0 && warp < kIntWarp0) {
-    for (int i = threadIdx.x - kEpiWarp0 * 32; i < PARAM_FLOATS; i += 128) {
+    for (int i = threadIdx.x - kEpiWarp0 * 32; i < PARAM_FLOATS; i += kEpiWarps * 32) {
       float v;
       if (i < N0) v = __ldg(p.b0 + i);
       else if (i < N0 + N1) v = __ldg(p.b1 + i - N0);
@@ -576,11 +578,14 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
   } else if (warp < kIntWarp0) {
     // =========================== epilogue warps ===========================
-    const int quarter = warp & 3;
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32 * (warp % 4) .. + 31): `half` selects the columns.
+    const int quarter = warp & 3, half = (warp - kEpiWarp0) >> 2;
     const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     const uint32_t hready_remote = mapa(hready_bar, 0);
     const float bias3 = __ldg(p.b3);
     const int r_in_tile = quarter * 32 + lane;
+    float* const s_part = reinterpret_cast<float*>(gbase + OFF_PART);
+    auto pair_sync = [&]() { named_bar_sync(3 + quarter, 64); };     // the two warps of this lane quarter
     auto arrive_hready = [&]() {
       __syncwarp();
       if (lane == 0) mbar_arrive_remote(hready_remote);
@@ -594,14 +599,18 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tile_rows(p.tm, 2u * pair + rank, p.n_tiles, g0, s_lo, s_hi);
       const bool live = r_in_tile >= s_lo && r_in_tile < s_hi;
       const int64_t orow = g0 + r_in_tile - p.tm.begin;
-      // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256) ----
+      // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256), compacted in place.  Step m: the pair reads accumulator
+      //      columns [64 m, +64) and writes H1 columns [32 m, +32); the pair barrier between the loads and the stores keeps a
+      //      warp from overwriting columns its partner has not read yet (step m's stores never reach a later step's loads). ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(itn, 6);
 #pragma unroll 1
-      for (int j = 0; j < N0 / 32; ++j) {
+      for (int m = 0; m < N0 / 64; ++m) {
+        const int j = 2 * m + half;
         uint32_t v[32], u[16];
         tmem_ld32(tq + j * 32, v);
+        pair_sync();
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 bb = *reinterpret_cast<const float2*>(s_b0 + j * 32 + 2 * i);
@@ -618,12 +627,13 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       if (estamp) stamp(itn, 7);
       arrive_hready();
-      // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) ----
+      // ---- after fc_1: H2 = relu(acc + b1) -> bf16 -> TMEM [0,128) (reads [256,512): no overlap) ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(itn, 8);
 #pragma unroll 1
-      for (int j = 0; j < N1 / 32; ++j) {
+      for (int m = 0; m < N1 / 64; ++m) {
+        const int j = half * (N1 / 64) + m;
         uint32_t v[32], u[16];
         tmem_ld32(tq + 256 + j * 32, v);
 #pragma unroll
@@ -638,13 +648,14 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       if (estamp) stamp(itn, 9);
       arrive_hready();
-      // ---- after fc_2: sdf = (relu(acc + b2) . w3 + b3) / out_div ----
+      // ---- after fc_2: sdf = (relu(acc + b2) . w3 + b3) / out_div; the upper column half hands its partial sum over ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(itn, 10);
       float2 acc2 = make_float2(0.f, 0.f);
 #pragma unroll 1
-      for (int j = 0; j < N2 / 32; ++j) {
+      for (int m = 0; m < N2 / 64; ++m) {
+        const int j = half * (N2 / 64) + m;
         uint32_t v[32];
         tmem_ld32(tq + 256 + j * 32, v);
 #pragma unroll
@@ -658,7 +669,10 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_before();
       if (estamp) stamp(itn, 11);
       arrive_hready();
-      if (live) p.sdf[orow] = __fdiv_rn((acc2.x + acc2.y) + bias3, p.out_div);
+      if (half == 1) s_part[r_in_tile] = acc2.x + acc2.y;
+      pair_sync();
+      if (half == 0 && live) p.sdf[orow] = __fdiv_rn(((acc2.x + acc2.y) + s_part[r_in_tile]) + bias3, p.out_div);
+      pair_sync();                                                  // s_part is free again
     }
   } else {
     // =========================== interp warps ===========================

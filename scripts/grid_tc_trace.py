@@ -23,14 +23,17 @@ def main():
     rows = min(rows, res ** 3 - begin)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
     stats = torch.zeros(2, device=dev, dtype=torch.int64)
+    G = ls.table(0, res, begin, rows)
+    X = ls.rest(0, res, begin, rows)
+    plan = ls.plan(0, res, begin, rows, G)
     for rep in range(3):
         stats.zero_()
         ev[0].record()
-        G = ls.table(0, res, begin, rows)
+        ls.table(0, res, begin, rows, out=G)
         ev[1].record()
-        X = ls.rest(0, res, begin, rows)
+        ls.rest(0, res, begin, rows, out=X)
         ev[2].record()
-        plan = ls.plan(0, res, begin, rows, G)
+        ls.plan(0, res, begin, rows, G, out=plan)
         ev[3].record()
         sdf, tr = ls.evaluate(res, begin, rows, X, plan, 10.0, trace=True, stats=stats)
         ev[4].record()
