@@ -71,10 +71,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
   }
 }
-// Whole-warp wait: lane 0 polls, the warp reconverges on __syncwarp (saves 31/32 of the spin issue slots).
+// Whole-warp wait: every lane waits on the barrier itself.  The try_wait is one warp instruction whatever the number of
+// active lanes, so this costs no more issue slots than polling from one lane -- and it avoids the divergent
+// `if (lane == 0) wait; __syncwarp()` form, whose reconvergence compiles to a WARPSYNC.COLLECTIVE / NANOSLEEP loop on
+// sm_100 that was measured to add up to ~2.5k cycles to a hand-off (profiles/r02_grid_tc_notes.md).
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
+  mbar_wait(bar, parity);
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
