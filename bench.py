@@ -36,7 +36,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    ap.add_argument("--no-gpu-library", action="store_true", help="skip the stock-PyTorch-on-GPU baseline of the main line")
+    ap.add_argument("--lib-chunks", type=int, default=8, help="65536-point chunks timed per mode for the stock-PyTorch GPU baseline")
     ap.add_argument("--res", type=int, default=256)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--chunk", type=int, default=0,
@@ -127,6 +129,93 @@ def cpu_reference_rate(res: int, chunks: int, warm: int = 1):
                            f"torch CPU {cores} threads")
 
 
+def gpu_library_rates(res: int, chunks: int, dev, trans: str = "camera"):
+    """SURVEY.md 8d "library Blackwell kernel bar": the reference's own op sequence (oracle/ref_port.py = the ATen calls of
+    network/modules.py:24-54, 255-282) on the SAME GPU through stock PyTorch / cuDNN / cuBLAS -- torch defaults (TF32
+    convolutions), TF32 off, bf16 autocast -- on `chunks` 65536-point chunks of the grid (reference executors.py:215-224),
+    plus the cfg-2 training step (8 x 2048 queries, forward + backward through stock autograd, reference losses.py:15-38).
+    Returns a dict of queries/s."""
+    import torch
+    from list_b200 import synth
+    from oracle import ref_port
+    from oracle.list_oracle import create_grid_points_from_bounds
+    out = {"unit": UNIT, "sample": f"{chunks} x {CPU_CHUNK}-point chunks of the {res}^3 grid after 2 warm-up chunks, stock PyTorch "
+                                    f"{torch.__version__} on the same GPU (per-image upsample re-run per chunk, as the reference does)"}
+    inp = synth.make_inputs(seed=synth.SEED, B=1, N=8, size="full", trans=trans).to(dev)
+    grid = torch.tensor(create_grid_points_from_bounds(-0.5, 0.5, res)[res ** 3 // 2: res ** 3 // 2 + (chunks + 2) * CPU_CHUNK]).unsqueeze(0).float().to(dev)
+    parts = torch.split(grid, CPU_CHUNK, 1)
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+
+    def run(autocast):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            for p in parts[:2]:
+                ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            n = 0
+            for p in parts[2:]:
+                ref_port.list_query(inp.maps, inp.vols, inp.trans_mat, p, inp.weights)
+                n += p.shape[1]
+            e1.record()
+            torch.cuda.synchronize()
+        return n / (e0.elapsed_time(e1) * 1e-3)
+
+    try:
+        out["tf32_default"] = run(False)
+        torch.backends.cudnn.allow_tf32 = False
+        torch.backends.cuda.matmul.allow_tf32 = False
+        out["tf32_off"] = run(False)
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+        out["bf16_autocast"] = run(True)
+        # cfg-2: training shape through stock autograd
+        B, N, scale = 8, 2048, 10.0
+        tr = synth.make_inputs(seed=synth.SEED, B=B, N=N, size="full", trans="camera", points="training").to(dev)
+        _, gt = synth.training_points(B, N, torch.Generator().manual_seed(synth.SEED + 1000))
+        gt = gt.to(dev)
+        maps = [m.clone().requires_grad_(True) for m in tr.maps]
+        vols = [v.clone().requires_grad_(True) for v in tr.vols]
+        T = tr.trans_mat.clone().requires_grad_(True)
+        w = {k: v.clone().requires_grad_(True) for k, v in tr.weights.items()}
+        leaves = [*maps, *vols, T, *w.values()]
+
+        def step():
+            for t in leaves:
+                t.grad = None
+            sdf = ref_port.list_query(maps, vols, T, tr.points, w)
+            ((gt * scale - sdf) ** 2).sum(-1).mean().backward()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out["cfg2_train_step_ms_tf32_default"] = e0.elapsed_time(e1) / 5
+        out["cfg2_train_queries_per_sec_tf32_default"] = B * N / (out["cfg2_train_step_ms_tf32_default"] * 1e-3)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+    return out
+
+
+def run_torch_gpu(a):
+    """`--impl torch_gpu`: the stock-PyTorch GPU baseline as a bench line of its own (rank 0 only)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    r = gpu_library_rates(a.res, max(a.steps, 1), dev)
+    print(json.dumps({
+        "impl": "torch_gpu", "metric": METRIC, "value": r["tf32_default"], "unit": UNIT, "n_gpus": 1, "steps": a.steps, "warmup": 2,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": f"cfg-4: 1 image, {a.res}^3 dense SDF grid, bounded sample per step", "sample": r["sample"]},
+        "gpu_library_baseline": r,
+    }), flush=True)
+
+
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -164,6 +253,8 @@ def main():
     a = parse()
     if a.impl == "reference":
         return run_reference(a)
+    if a.impl == "torch_gpu":
+        return run_torch_gpu(a)
 
     import torch
     import torch.distributed as dist
@@ -410,6 +501,13 @@ def main():
         v, cores, sample = cpu_reference_rate(res, a.cpu_chunks)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
+    lib_gpu = None
+    if rank == 0 and world == 1 and not a.no_gpu_library:
+        del ws, local_out
+        main_run.clear()
+        torch.cuda.empty_cache()
+        lib_gpu = gpu_library_rates(res, a.lib_chunks, dev, a.trans)
+
     kernel_path = {"lines": "projection once per image; per chunk: hoist_lines_kernel (per-line column tables of the projected "
                             "levels), grid_plan_kernel (row lists + interpolation weights per tile), hoist_rest_kernel "
                             "(non-hoisted feature columns), grid_tc_kernel (interpolation of the "
@@ -432,6 +530,7 @@ def main():
                        "parallelism": f"grid-shard x{world}"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": a.steps * launches_per_step,
             "roofline": dominant, "roofline_other": other, "other_transform": other_T, "cpu_baseline": cpu,
+            "gpu_library_baseline": lib_gpu,
             "checksum": checksum,
         }), flush=True)
     if world > 1:

@@ -496,3 +496,55 @@ def test_parity_gate_cfg4_strided_subsample_of_256_cubed():
         err = (full.cpu()[idx] - ref).abs()
         print(f"cfg-4 256^3 subsample, {mode}: max|dSDF|/scale {err.max().item():.2e} over {idx.numel()} points")
         assert err.max().item() <= tol
+
+
+def test_parity_gate_cfg3_128_cubed_grid_and_mesh_topology():
+    """cfg-3: the whole 128^3 grid on the GPU in both precisions; every 64th point against the oracle, and -- the
+    north_star's "identical marching-cubes topology on the fp32 path" -- the marching-cubes case index of every cell of a
+    dense 4-plane slab of the grid (65 536 vertices evaluated by the oracle) on the fp32 grid."""
+    inp = _camera_inputs()
+    res, stride = 128, 64
+    g = inp.to(DEV)
+    idx = torch.arange(3, res ** 3, stride)
+    pts = hotpath.grid_points(res).cpu()
+    with torch.no_grad():
+        ref = P.list_query(inp.maps, inp.vols, inp.trans_mat, pts[idx].unsqueeze(0), inp.weights)[0] / 10.0
+        x0 = 61
+        slab = slice(x0 * res * res, (x0 + 4) * res * res)
+        ref_slab = (P.list_query(inp.maps, inp.vols, inp.trans_mat, pts[slab].unsqueeze(0), inp.weights)[0] / 10.0).view(4, res, res).numpy()
+    for mode, tol in (("bf16", BF16_TOL / 10.0), ("fp32", FP32_TOL / 10.0)):
+        ctx, kw = ctx_and_weights(g, mode)
+        full = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=524288 if mode == "bf16" else 131072)[0].cpu()
+        err = (full[idx] - ref).abs().max().item()
+        got_slab = full[slab].view(4, res, res).numpy()
+        changed = int((O.mc_case_index(got_slab) != O.mc_case_index(ref_slab)).sum())
+        print(f"cfg-3 128^3, {mode}: max|dSDF|/scale {err:.2e} over {idx.numel()} points; marching-cubes cells changed in the slab: {changed}")
+        assert err <= tol
+        if mode == "fp32":
+            flipped = np.sign(got_slab) != np.sign(ref_slab)
+            assert np.all(np.abs(ref_slab[flipped]) <= FP32_TOL / 10.0)
+            assert changed == int(flipped.any()) * changed              # cells may only change through a listed sign flip
+            assert changed == 0 or flipped.sum() > 0
+
+
+def test_parity_gate_cfg5_eight_images_per_gpu():
+    """cfg-5: one call over B = 8 full-size images (the per-GPU share of 64 images on 8 B200), 128^3 each, bf16 line-table
+    path; 4 096 strided points of every image against the oracle."""
+    B, res, stride = 8, 128, 512
+    inp = synth.make_inputs(seed=synth.SEED + 5, B=B, N=8, size="full", trans="camera")
+    g = inp.to(DEV)
+    ctx, kw = ctx_and_weights(g, "bf16")
+    full = hotpath.grid_sdf(ctx, kw, res, sdf_scale=10.0, chunk_rows=1048576).cpu()
+    assert full.shape == (B, res ** 3)
+    idx = torch.arange(7, res ** 3, stride)
+    pts = hotpath.grid_points(res).cpu()[idx].unsqueeze(0).expand(B, -1, -1).contiguous()
+    with torch.no_grad():
+        ref = P.list_query(inp.maps, inp.vols, inp.trans_mat, pts, inp.weights) / 10.0
+    err = (full[:, idx] - ref).abs()
+    print(f"cfg-5 8 x 128^3 bf16: max|dSDF|/scale per image {[f'{e:.1e}' for e in err.max(dim=1).values.tolist()]}")
+    assert err.max().item() <= BF16_TOL / 10.0
+    # image b of the batch equals the same image evaluated alone (no cross-image state in the hoisted tensors)
+    one = synth.HotPathInputs([m[3:4] for m in g.maps], [v[3:4] for v in g.vols], g.trans_mat[3:4], g.points[3:4], g.weights)
+    ctx1, _ = ctx_and_weights(one, "bf16")
+    alone = hotpath.grid_sdf(ctx1, kw, res, begin=res ** 3 // 2, count=65536, sdf_scale=10.0, chunk_rows=65536).cpu()
+    assert torch.equal(alone[0], full[3, res ** 3 // 2: res ** 3 // 2 + 65536])
