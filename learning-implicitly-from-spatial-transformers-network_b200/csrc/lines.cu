@@ -43,10 +43,27 @@ struct DispGeo {                        // per (level, displacement) of a CTA
   int yn[kNY];                          // H node indices (clamped to the volume)
 };
 
+// 4 consecutive bf16 channels (8-byte access)
+__device__ __forceinline__ void load4(const __nv_bfloat16* __restrict__ p, float v[4]) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* __restrict__ p, const float v[4]) {
+  uint2 u;
+  u.x = pack_bf16x2(v[0], v[1]);
+  u.y = pack_bf16x2(v[2], v[3]);
+  *reinterpret_cast<uint2*>(p) = u;
+}
+
+// Thread = (table row node i, 4-channel vector): 128 threads cover the 512 channels of a row, a CTA of 256 threads works
+// on two nodes at a time.  Per displacement the thread reduces the 2 (D) x kNY (H) projected rows to kNY rows once and
+// then takes every line's H-interpolation from them; when all lines of the CTA lie in one H cell (`two`: the third
+// node has zero weight everywhere) the third row is neither loaded nor multiplied.
 template <int LY>
-__global__ void __launch_bounds__(kLinesThreads, LY >= 8 ? 1 : 2) hoist_lines_kernel(const LinesParams p) {
+__global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const LinesParams p) {
   __shared__ DispGeo s_geo[kMaxLev][LIST_NUM_DISP];
-  __shared__ __align__(16) float s_wy[kMaxLev][LIST_NUM_DISP][LY][4];        // H weights of every line on the kNY nodes (4th: pad)
+  __shared__ __align__(16) float s_wy[kMaxLev][LIST_NUM_DISP][LY][4];        // H weights of every line on the kNY nodes; [3]: 1 if node 2 is unused
   const int tid = threadIdx.x;
   const int res = p.tm.res;
   const unsigned plane = blockIdx.x / static_cast<unsigned>(p.groups);
@@ -66,20 +83,22 @@ __global__ void __launch_bounds__(kLinesThreads, LY >= 8 ? 1 : 2) hoist_lines_ke
     g.z1 = static_cast<uint32_t>(az.i1) * R * R * kN0L;
     g.wz0 = az.w0; g.wz1 = az.w1;
     int ybase = 0;
+    bool two = true;
     for (int j = 0; j < LY; ++j) {
       const int ly = min(ly0 + j, res - 1);
       q[1] = linspace_f32_step(ly, res, p.tm.bb_min, p.tm.bb_max, p.tm.step) * 2.0f;
       displaced(q, d, pd);
       const Axis3 ay = axis_border(pd[1], R);
       if (j == 0) ybase = ay.i0;
-      float w[4] = {0.f, 0.f, 0.f, 0.f};
       // i0 - ybase is 0 or 1 (the lines of a CTA span less than one cell); i1 == i0 only at the border, where w1 == 0
-      const int r0 = ay.i0 - ybase;
-      w[r0] += ay.w0;
-      w[r0 + (ay.i1 - ay.i0)] += ay.w1;
+      const int r0 = ay.i0 - ybase, r1 = r0 + (ay.i1 - ay.i0);
+      float w[3];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) s_wy[h][d][j][k] = w[k];
+      for (int k = 0; k < 3; ++k) w[k] = (k == r0 ? ay.w0 : 0.f) + (k == r1 ? ay.w1 : 0.f);
+      two = two && w[2] == 0.f;
+      s_wy[h][d][j][0] = w[0]; s_wy[h][d][j][1] = w[1]; s_wy[h][d][j][2] = w[2];
     }
+    for (int j = 0; j < LY; ++j) s_wy[h][d][j][3] = two ? 1.f : 0.f;
 #pragma unroll
     for (int k = 0; k < kNY; ++k) g.yn[k] = min(ybase + k, R - 1);
     s_geo[h][d] = g;
@@ -96,50 +115,63 @@ __global__ void __launch_bounds__(kLinesThreads, LY >= 8 ? 1 : 2) hoist_lines_ke
   }
   if (jlo >= jhi) return;
   const int64_t out_line0 = lz * res + ly0 - p.line_first;       // may be negative for the lines below jlo
-  const int v = tid & 63, ig = tid >> 6;                        // 8-channel vector, node group
-  // items: (level, node); thread = (node mod 4, vector)
+  const int v = tid & 127, ig = tid >> 7;                        // 4-channel vector, node group
   for (int h = 0; h < p.nh; ++h) {
     const int R = p.R[h];
-    const __nv_bfloat16* __restrict__ pv = p.pvol[h] + v * 8;
+    const __nv_bfloat16* __restrict__ pv = p.pvol[h] + v * 4;
     const uint32_t ds = p.dstride[h];
-    for (int i = ig; i < R; i += kLinesThreads / 64) {
+    for (int i = ig; i < R; i += kLinesThreads / 128) {
       const uint32_t ioff = static_cast<uint32_t>(i) * kN0L;
 #pragma unroll 1
       for (int cls = 0; cls < 3; ++cls) {
-        float acc[LY][8];
+        float acc[LY][4];
 #pragma unroll
         for (int j = 0; j < LY; ++j)
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[j][c] = 0.f;
+          for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
         const int nd = cls == 0 ? 5 : 1;
 #pragma unroll 1
         for (int di = 0; di < nd; ++di) {
           const int d = cls == 0 ? (di == 0 ? 0 : di + 2) : cls;
           const DispGeo& g = s_geo[h][d];
           const __nv_bfloat16* __restrict__ pd = pv + static_cast<size_t>(d) * ds + ioff;
-          float t0[kNY][8], t1[kNY][8];
+          const bool two = s_wy[h][d][0][3] != 0.f;                 // uniform over the CTA
+          float u[kNY][4];
+          {
+            float t0[kNY][4], t1[kNY][4];
 #pragma unroll
-          for (int k = 0; k < kNY; ++k) {
-            const uint32_t yo = static_cast<uint32_t>(g.yn[k]) * R * kN0L;
-            load8(pd + g.z0 + yo, t0[k]);
-            load8(pd + g.z1 + yo, t1[k]);
+            for (int k = 0; k < kNY; ++k) {
+              if (k < 2 || !two) {
+                const uint32_t yo = static_cast<uint32_t>(g.yn[k]) * R * kN0L;
+                load4(pd + g.z0 + yo, t0[k]);
+                load4(pd + g.z1 + yo, t1[k]);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < kNY; ++k)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) u[k][c] = (k < 2 || !two) ? fmaf(t1[k][c], g.wz1, t0[k][c] * g.wz0) : 0.f;
           }
-          float u[kNY][8];
+          if (two) {
 #pragma unroll
-          for (int k = 0; k < kNY; ++k)
+            for (int j = 0; j < LY; ++j) {
+              const float2 w = *reinterpret_cast<const float2*>(s_wy[h][d][j]);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) u[k][c] = fmaf(t1[k][c], g.wz1, t0[k][c] * g.wz0);
+              for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(u[1][c], w.y, fmaf(u[0][c], w.x, acc[j][c]));
+            }
+          } else {
 #pragma unroll
-          for (int j = 0; j < LY; ++j) {
-            const float4 w = *reinterpret_cast<const float4*>(s_wy[h][d][j]);
+            for (int j = 0; j < LY; ++j) {
+              const float4 w = *reinterpret_cast<const float4*>(s_wy[h][d][j]);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[j][c] = fmaf(u[2][c], w.z, fmaf(u[1][c], w.y, fmaf(u[0][c], w.x, acc[j][c])));
+              for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(u[2][c], w.z, fmaf(u[1][c], w.y, fmaf(u[0][c], w.x, acc[j][c])));
+            }
           }
         }
         const size_t row = static_cast<size_t>(p.rowbase[h] + cls * R + i);
 #pragma unroll
         for (int j = 0; j < LY; ++j)
-          if (j >= jlo && j < jhi) store8(p.G + (static_cast<size_t>(out_line0 + j) * p.rpl + row) * kN0L + v * 8, acc[j]);
+          if (j >= jlo && j < jhi) store4(p.G + (static_cast<size_t>(out_line0 + j) * p.rpl + row) * kN0L + v * 4, acc[j]);
       }
     }
   }
