@@ -286,12 +286,16 @@ def main():
         ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, a.dtype)
         kw = hotpath.prepare_weights(g.weights, ctx.layout, a.dtype)
         ws = hotpath._workspace(ctx.struct(), kw.struct(), chunk, dev)
-        local_out = torch.empty(1, count, device=dev, dtype=torch.float32)
+        # the kernels write the rank's shard straight into its piece of the all_gather input (no staging copies)
+        shard_buf, local_out = parallel.shard_buffer(total, rank, world, 1, dev, align=res * res)
+        local_out = local_out if local_out.is_contiguous() else local_out.contiguous()
+        gathered = torch.empty(world, shard_buf.shape[1], device=dev, dtype=torch.float32) if world > 1 else None
 
         def step():
             hotpath.grid_sdf(ctx, kw, res, begin, count, SDF_SCALE, chunk, out=local_out, workspace=ws)
             if world > 1:
-                return parallel.gather_shards(local_out, total, world, align=res * res)
+                src = shard_buf if local_out.data_ptr() == shard_buf.data_ptr() else local_out
+                return parallel.gather_shards(src, total, world, align=res * res, out=gathered)
             return local_out
 
         for _ in range(max(warmup, 3)):

@@ -10,6 +10,9 @@ import torch
 import torch.distributed as dist
 
 
+COARSE_MAX_RES = 32      # levels up to this resolution are read by the projection (csrc/api.cu kLinesMaxRes) and cannot be late
+
+
 def shard_range(total: int, rank: int, world: int, align: int = 1) -> Tuple[int, int]:
     """[begin, count) of `rank`: equal contiguous ranges, boundaries rounded to `align`
     (the last rank takes the remainder)."""
@@ -19,17 +22,35 @@ def shard_range(total: int, rank: int, world: int, align: int = 1) -> Tuple[int,
     return begin, max(0, min(total, begin + per) - begin)
 
 
-def gather_shards(local: torch.Tensor, total: int, world: int, align: int = 1, group=None) -> torch.Tensor:
-    """local: (B, count_r) fp32 shard of every image -> (B, total) on every rank, one collective."""
+def gather_shards(local: torch.Tensor, total: int, world: int, align: int = 1, group=None,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """local: (B, count_r) fp32 shard of every image -> (B, total) on every rank, ONE collective (all_gather of equal
+    pieces of `per` = the aligned shard size).  When `local` already is a (B, per) buffer -- the caller let the kernels
+    write straight into it (shard_buffer) -- nothing is staged; `out` (world * B, per) is reused if given."""
     if world == 1:
         return local
     B = local.shape[0]
     per = shard_range(total, 0, world, align)[1]
-    buf = torch.zeros(B, per, device=local.device, dtype=local.dtype)
-    buf[:, :local.shape[1]] = local
-    out = torch.empty(world * B, per, device=local.device, dtype=local.dtype)      # rank-major concat on dim 0
-    dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
+    if local.shape[1] == per and local.is_contiguous():
+        buf = local
+    else:
+        buf = torch.zeros(B, per, device=local.device, dtype=local.dtype)
+        buf[:, :local.shape[1]] = local
+    if out is None:
+        out = torch.empty(world * B, per, device=local.device, dtype=local.dtype)      # rank-major concat on dim 0
+    dist.all_gather_into_tensor(out, buf, group=group)
+    if B == 1 and world * per == total:
+        return out.view(1, total)                                                       # already the grid, no copy
     return out.view(world, B, per).permute(1, 0, 2).reshape(B, world * per)[:, :total].contiguous()
+
+
+def shard_buffer(total: int, rank: int, world: int, B: int, device, align: int = 1):
+    """(buffer (B, per), view (B, count_r)): let the evaluation write its shard into `view`; `buffer` then goes into
+    gather_shards without a staging copy (the tail of the last rank's buffer stays zero)."""
+    per = shard_range(total, 0, world, align)[1]
+    count = shard_range(total, rank, world, align)[1]
+    buf = torch.zeros(B, per, device=device, dtype=torch.float32)
+    return buf, buf[:, :count]
 
 
 def sharded_grid(evaluate: Callable[[int, int], torch.Tensor], total: int, align: int = 1, group=None) -> torch.Tensor:
@@ -58,9 +79,9 @@ def rebuild_from_gathered(gathered: torch.Tensor, per, fulls) -> None:
 
 def upload_stages(vol_res, n_maps: int, n_tensors: int):
     """Index lists (into [*maps, *vols, T]) of the two upload stages of the staged end-to-end path: everything the
-    projection and the first addend gather read (maps, levels with R <= 16, T), then the fine levels.  Returns
+    projection and the first chunk's line tables read (maps, levels with R <= 32, T), then the fine levels.  Returns
     (stages, late_levels); a stage is dropped if empty."""
-    late_levels = [l for l, r in enumerate(vol_res) if r > 16]
+    late_levels = [l for l, r in enumerate(vol_res) if r > COARSE_MAX_RES]
     late_idx = {n_maps + l for l in late_levels}
     stages = [[i for i in range(n_tensors) if i not in late_idx], sorted(late_idx)]
     return [st for st in stages if st], late_levels
@@ -118,7 +139,7 @@ class ShardedHostRunner:
         self.out_dev = torch.empty(trans_host.shape[0], self.count, device=dev, dtype=torch.float32)
         self.out_host = torch.empty(trans_host.shape[0], self.count, dtype=torch.float32).pin_memory()
         self.per = [-(-t.numel() // self.world) for t in self.hosts]           # elements of every rank's slice
-        # Two stages (same idea as list_sdf_grid_host): the coarse tensors -- maps, levels with R <= 16, T,
+        # Two stages (same idea as list_sdf_grid_host): the coarse tensors -- maps, levels with R <= 32, T,
         # all the projection and the first addend gather read -- are uploaded and all-gathered first; the fine levels
         # follow on a side stream while those kernels run, and list_sdf_grid_late prepares them when they are there.
         stage_idx, self.late_levels = upload_stages([v.shape[2] for v in vols_host], self.n_maps, len(self.hosts))

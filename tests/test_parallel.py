@@ -91,7 +91,7 @@ def _stage_worker(rank, world, port, q):
     try:
         g = torch.Generator().manual_seed(7)                      # same tensors on every rank
         maps = [torch.rand(1, 4, 6, 6, generator=g), torch.rand(1, 8, 3, 3, generator=g)]
-        vols = [torch.rand(1, 1, 32, 32, 32, generator=g), torch.rand(1, 3, 20, 20, 20, generator=g),
+        vols = [torch.rand(1, 1, 40, 40, 40, generator=g), torch.rand(1, 3, 36, 36, 36, generator=g),
                 torch.rand(1, 8, 16, 16, 16, generator=g), torch.rand(1, 8, 5, 5, 5, generator=g)]
         T = torch.rand(1, 4, 3, generator=g)
         hosts = [*maps, *vols, T]
@@ -112,7 +112,7 @@ def _stage_worker(rank, world, port, q):
 
 def test_staged_upload_gloo_world2():
     """The two-stage upload of the multi-rank end-to-end path: after stage 1 exactly the coarse tensors (maps, levels
-    with R <= 16, T) are complete on every rank, after stage 2 all of them."""
+    with R <= 32, T) are complete on every rank, after stage 2 all of them."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
