@@ -40,12 +40,20 @@ def test_hot_modules_with_the_reference_signatures():
     pool = modules.PerceptualPooling()
     dec = modules.VoxelDecoder2(inp.feature_size, 256).to(DEV)
     dec.load_state_dict({k: v for k, v in g.weights.items()})
-    percep = pool(g.maps, q, g.trans_mat)
+    with torch.no_grad():                                                  # executors.py:199 (the test loop runs under no_grad)
+        percep = pool(g.maps, q, g.trans_mat)
+        assert pool(g.maps, q[:, :100].contiguous(), g.trans_mat).shape == (2, 1024, 1, 100)     # second chunk: cached context
     assert percep.shape == (2, 1024, 1, 300)
     qc = q.cpu()
     ref_p = P.perceptual_pooling(inp.maps, qc, inp.trans_mat)
     assert (percep.cpu() - ref_p).abs().max().item() <= 2e-5
-    sdf = dec(q, g.vols, percep.reshape(2, -1, 300))
+    # the stand-alone modules run the kernels on detached tensors: under autograd they refuse instead of training nothing
+    with pytest.raises(RuntimeError, match="inference-only"):
+        dec(q, g.vols, percep.reshape(2, -1, 300))
+    with pytest.raises(RuntimeError, match="inference-only"):
+        pool([m.clone().requires_grad_(True) for m in g.maps], q, g.trans_mat)
+    with torch.no_grad():
+        sdf = dec(q, g.vols, percep.reshape(2, -1, 300))
     assert sdf.shape == (2, 300)
     ref = P.voxel_decoder2(qc, inp.vols, ref_p.reshape(2, -1, 300), inp.weights)
     assert (sdf.cpu() - ref).abs().max().item() <= 1e-4
