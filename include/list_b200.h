@@ -152,10 +152,16 @@ LIST_API int list_gather_grid_fwd(const ListCtx* ctx, int32_t image, int32_t res
 /* a-6 (reference modules.py:276-282): sdf[r] = fc_out(relu(fc_2(relu(fc_1(relu(fc_0 X[r]))))))
  * for `rows` feature rows; result divided by out_div (1 = the reference's scaled SDF,
  * sdf_scale = executors.py:231).  LIST_BF16: tcgen05/TMEM kernel, needs no workspace.
- * LIST_F32: FFMA kernels, workspace >= list_mlp_workspace_bytes(). */
+ * LIST_F32: 3xTF32 tcgen05 GEMMs (fp32-level accuracy), workspace >= list_mlp_workspace_bytes(). */
 LIST_API size_t list_mlp_workspace_bytes(const ListWeights* w, int64_t rows);
 LIST_API int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf,
                  float out_div, void* workspace, size_t workspace_bytes, void* stream);
+/* LIST_F32 forward of a TRAINING step (the activations it leaves in `workspace` feed list_sdf_bwd).  list_mlp_fwd computes
+ * the fp32 mode on the tensor cores (three TF32 products per fp32 product, csrc/tgemm.cu), whose truncating accumulation
+ * is inside the 1e-4 SDF bound but can flip the ReLU mask of units within 1e-5 of zero; this twin accumulates on the
+ * FFMA pipe (round to nearest) so that the saved masks -- and with them the gradients -- match the fp32 reference. */
+LIST_API int list_mlp_fwd_train(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf,
+                       float out_div, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Diagnostic twin of list_mlp_fwd for the bf16 tensor-core kernel: additionally copies the hidden
  * activations relu(fc_0) [rows][n0], relu(fc_1) [rows][n1], relu(fc_2) [rows][n2] (fp32, before the
@@ -286,6 +292,13 @@ LIST_API int list_mc_count(const float* sdf, int32_t res, float iso, int32_t neg
 LIST_API int list_mc_generate(const float* sdf, int32_t res, float iso, int32_t negate, const void* workspace,
                      size_t workspace_bytes, float* vertices, int64_t n_vertices, int32_t* triangles,
                      int64_t n_triangles, void* stream);
+
+/* The GEMM of the fp32 path (a-6 in LIST_F32 mode and its backward; reference modules.py:276-280 and autograd): fp32-level
+ * accuracy on the tensor cores through three TF32 products per fp32 product (csrc/tgemm.cu).  Exposed for tests:
+ *   C[m][n] (+)= sum_k A[m*lda + k] B[n*ldb + k]   (both operands K-major; the backward transposes what comes otherwise)
+ * lo_workspace: >= 4 * (M*lda + N*ldb) bytes (the low-order parts of both operands). */
+LIST_API int list_gemm_f32_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N,
+                     int32_t K, int32_t accumulate, float* lo_workspace, size_t lo_bytes, void* stream);
 
 /* a-9 backward of a-2..a-6 for training (reference train.py:72-85 via autograd):
  * given d_sdf[B*N] computes all gradients in ListGrads (fp32 path only).

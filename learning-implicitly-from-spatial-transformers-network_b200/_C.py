@@ -71,6 +71,7 @@ SIGNATURES = {
     "list_gather_grid_fwd": (C.c_int, [_P(ListCtx), _i32, _i32, _f64, _f64, _i64, _i64, _vp, _i64, _vp]),
     "list_mlp_workspace_bytes": (_sz, [_P(ListWeights), _i64]),
     "list_mlp_fwd": (C.c_int, [_P(ListWeights), _vp, _i64, _i64, _vp, _f32, _vp, _sz, _vp]),
+    "list_mlp_fwd_train": (C.c_int, [_P(ListWeights), _vp, _i64, _i64, _vp, _f32, _vp, _sz, _vp]),
     "list_mlp_fwd_debug": (C.c_int, [_P(ListWeights), _vp, _i64, _i64, _vp, _f32, _vp, _vp, _vp, _vp]),
     "list_hoist_bytes": (_sz, [_P(ListCtx), _P(ListWeights)]),
     "list_hoist_layout": (C.c_int, [_P(ListCtx), _P(ListWeights), _P(_i32), _P(_i32)]),
@@ -101,6 +102,7 @@ SIGNATURES = {
     "list_mc_workspace_bytes": (_sz, [_i32]),
     "list_mc_count": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _sz, _vp, _vp]),
     "list_mc_generate": (C.c_int, [_vp, _i32, _f32, _i32, _vp, _sz, _vp, _i64, _vp, _i64, _vp]),
+    "list_gemm_f32_tc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _sz, _vp]),
     "list_bwd_workspace_bytes": (_sz, [_P(ListWeights), _i64]),
     "list_sdf_bwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _i64, _vp, _i64, _vp, _vp, _P(ListGrads),
                                _vp, _sz, _vp]),

@@ -7,6 +7,7 @@
 
 #include "common.cuh"
 #include "hoist.cuh"
+#include "tgemm.cuh"
 
 namespace list {
 
@@ -35,7 +36,7 @@ int gather_grid_walk(const ListCtx* ctx, int image, int res, double bb_min, doub
 int grid_points(float* q, int res, double lo, double hi, int64_t begin, int64_t count, cudaStream_t st);
 size_t mlp_f32_workspace_bytes(const ListWeights* w, int64_t rows);
 int mlp_f32_fwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows, float* sdf, float out_div, float* ws,
-                cudaStream_t st);
+                int exact, cudaStream_t st);
 size_t mlp_f32_bwd_workspace_bytes(const ListWeights* w, int64_t rows);
 int mlp_f32_bwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows, const float* fwd_ws, const float* d_sdf,
                 const ListGrads* g, float* ws, cudaStream_t st);
@@ -46,6 +47,7 @@ int mlp_tc_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, f
 int mlp_tc_fwd_hoisted(const ListWeights* w, int col0, int k, const void* Xh, int64_t ldx, int64_t rows, float* sdf,
                        float out_div, int variant, float* dbg1, float* dbg2, float* dbg3, long long* trace, cudaStream_t st);
 
+size_t mlp_f32_workspace_bytes(const ListWeights* w, int64_t rows);
 static size_t elem_size(int dtype) { return dtype == LIST_BF16 ? 2 : 4; }
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
@@ -347,8 +349,8 @@ size_t list_mlp_workspace_bytes(const ListWeights* w, int64_t rows) {
   return w->dtype == LIST_F32 ? mlp_f32_workspace_bytes(w, rows) : 0;
 }
 
-int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, void* workspace,
-                 size_t workspace_bytes, void* stream) {
+static int mlp_fwd_impl(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, void* workspace,
+                        size_t workspace_bytes, int exact, void* stream) {
   int rc = check_weights(w, -1);
   if (rc) return rc;
   LIST_CHECK_ARG(rows >= 0, "list_mlp_fwd: rows < 0");
@@ -364,9 +366,20 @@ int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows,
       set_error("list_mlp_fwd: workspace %zu B < required %zu B", workspace_bytes, need);
       return LIST_ENOMEM;
     }
-    return mlp_f32_fwd(w, static_cast<const float*>(X), ldx, rows, sdf, out_div, static_cast<float*>(workspace), st);
+    return mlp_f32_fwd(w, static_cast<const float*>(X), ldx, rows, sdf, out_div, static_cast<float*>(workspace), exact, st);
   }
   return mlp_tc_fwd(w, X, ldx, rows, sdf, out_div, mlp_variant(), nullptr, nullptr, nullptr, st);
+}
+
+int list_mlp_fwd(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+  return mlp_fwd_impl(w, X, ldx, rows, sdf, out_div, workspace, workspace_bytes, 0, stream);
+}
+
+int list_mlp_fwd_train(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  LIST_CHECK_ARG(w != nullptr && w->dtype == LIST_F32, "list_mlp_fwd_train: the training path is fp32");
+  return mlp_fwd_impl(w, X, ldx, rows, sdf, out_div, workspace, workspace_bytes, 1, stream);
 }
 
 int list_mlp_fwd_debug(const ListWeights* w, const void* X, int64_t ldx, int64_t rows, float* sdf, float out_div,
@@ -845,7 +858,11 @@ static void plan_host(const int32_t* map_ch, const int32_t* map_in, int n_maps, 
       if (vol_res[l] <= kLinesMaxRes) h += align_up(static_cast<size_t>(7) * B * vol_res[l] * vol_res[l] * vol_res[l] * 512 * 2, 256);
     ws += h + 256;
   }
-  if (dtype == LIST_F32) ws += align_up(static_cast<size_t>(chunk_rows) * (512 + 256 + 256) * 4, 256);
+  if (dtype == LIST_F32) {                             // activations + lo copies of the fp32 MLP (mlp_f32_workspace_bytes)
+    ListWeights wdim{};
+    wdim.dtype = LIST_F32; wdim.k_pad = lay.k_pad; wdim.n0 = 512; wdim.n1 = 256; wdim.n2 = 256;
+    ws += align_up(mlp_f32_workspace_bytes(&wdim, chunk_rows), 256);
+  }
   p->ws = take(ws);
   p->total = off;
 }
@@ -956,6 +973,27 @@ int list_sdf_grid_host(const float* const* maps_host, const int32_t* map_ch, con
   LIST_CUDA(cudaEventRecord(pp->cdone, pp->cp));
   LIST_CUDA(cudaStreamWaitEvent(st, pp->cdone, 0));
   return LIST_OK;
+}
+
+// ---- fp32-accurate tensor-core GEMM, exposed for tests ------------------------------------------------
+int list_gemm_f32_tc(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int32_t M, int32_t N, int32_t K,
+                     int32_t accumulate, float* lo_workspace, size_t lo_bytes, void* stream) {
+  LIST_CHECK_ARG(A && B && C && lo_workspace && M >= 1 && N >= 1 && K >= 1, "list_gemm_f32_tc: NULL argument or empty problem");
+  const int64_t a_elems = static_cast<int64_t>(M) * lda, b_elems = static_cast<int64_t>(N) * ldb;
+  LIST_CHECK_ARG(lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0, "list_gemm_f32_tc: leading dimensions must be multiples of 4");
+  if (lo_bytes < static_cast<size_t>(a_elems + b_elems) * 4) {
+    set_error("list_gemm_f32_tc: lo workspace %zu B < required %zu B", lo_bytes, static_cast<size_t>(a_elems + b_elems) * 4);
+    return LIST_ENOMEM;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* Alo = lo_workspace;
+  float* Blo = lo_workspace + a_elems;
+  int rc;
+  if ((rc = split_lo(A, Alo, a_elems, st))) return rc;
+  if ((rc = split_lo(B, Blo, b_elems, st))) return rc;
+  GemmEpilogue ep{};
+  ep.accumulate = accumulate;
+  return tgemm(A, Alo, lda, B, Blo, ldb, C, ldc, M, N, K, ep, st);
 }
 
 // ---- backward ------------------------------------------------------------------------------

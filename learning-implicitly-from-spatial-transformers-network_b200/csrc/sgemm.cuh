@@ -1,8 +1,6 @@
-// fp32 FFMA GEMM family used by the fp32 parity path of the implicit MLP (a-6, reference
-// network/modules.py:276-282) and by its backward (a-9).  tcgen05 has no true-fp32 MMA
-// (kind::tf32 keeps 10 mantissa bits, which does not meet the 1e-4 parity bound over K=3610),
-// so the fp32 mode stays on the FFMA pipe; the throughput path is the bf16 tcgen05 kernel in
-// mlp_tc.cu.
+// fp32 FFMA GEMM family: the reference implementation (LIST_B200_F32_TC=0) of the fp32 parity path of the implicit MLP
+// (a-6, reference network/modules.py:276-282) and of its backward (a-9).  The default is tgemm.cu, which reaches the same
+// accuracy on the tensor cores with three TF32 products per fp32 product.
 //
 //   C[m][n] (+)= epi( sum_k A(m,k) * B(k,n) )
 //   A_KMAJOR : A(m,k) = A[m*lda + k]   else A(m,k) = A[k*lda + m]
@@ -13,16 +11,9 @@
 // plain accumulation (accumulate = 1, no bias / ReLU / mask), which is what the launcher enforces.
 #pragma once
 #include "common.cuh"
+#include "tgemm.cuh"
 
 namespace list {
-
-struct GemmEpilogue {
-  const float* bias;      // [N] added before the activation, or nullptr
-  int relu;               // max(x,0)
-  const float* mask;      // [M][ldmask]: result *= (mask > 0), or nullptr (ReLU backward)
-  int64_t ldmask;
-  int accumulate;         // C += result
-};
 
 template <bool A_KMAJOR, bool B_KMAJOR>
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t lda,

@@ -363,8 +363,9 @@ class LineTableState:
         return out[0] if len(out) == 1 else tuple(out)
 
 
-def mlp(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0, return_workspace: bool = False):
-    """Row a-6 on feature rows X (rows, ldx)."""
+def mlp(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0, return_workspace: bool = False, train: bool = False):
+    """Row a-6 on feature rows X (rows, ldx).  train=True (fp32 only): the forward of a training step (list_mlp_fwd_train),
+    whose saved activations feed the backward."""
     dev = _require_cuda(X, weights.w0)
     if _DTYPE_CODE.get(X.dtype) != weights.dtype:
         raise ValueError(f"X dtype {X.dtype} does not match the weights' dtype code {weights.dtype}")
@@ -375,8 +376,9 @@ def mlp(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0, return_wo
     need = lib.list_mlp_workspace_bytes(C.byref(ws_struct), rows)
     ws = torch.empty(max(need, 16), device=dev, dtype=torch.uint8)
     with torch.cuda.device(dev):
-        _C.check(lib.list_mlp_fwd(C.byref(ws_struct), X.data_ptr(), X.stride(0), rows, sdf.data_ptr(), float(out_div),
-                                  ws.data_ptr(), ws.numel(), _stream()), "list_mlp_fwd")
+        fn = lib.list_mlp_fwd_train if train else lib.list_mlp_fwd
+        _C.check(fn(C.byref(ws_struct), X.data_ptr(), X.stride(0), rows, sdf.data_ptr(), float(out_div),
+                    ws.data_ptr(), ws.numel(), _stream()), "list_mlp_fwd")
     return (sdf, ws) if return_workspace else sdf
 
 
@@ -540,7 +542,7 @@ class _SdfFunction(torch.autograd.Function):
         pts = points.detach().to(torch.float32).contiguous()
         B, N, _ = pts.shape
         X = gather_features(hp, pts, raw)
-        sdf, ws = mlp(kw, X, 1.0, return_workspace=True)
+        sdf, ws = mlp(kw, X, 1.0, return_workspace=True, train=True)
         ctx.hp, ctx.kw, ctx.lay, ctx.raw = hp, kw, lay, raw
         ctx.save_for_backward(pts, X, ws)
         ctx.shapes = (w0.shape, w1.shape, w2.shape, w3.shape)
@@ -649,6 +651,20 @@ def query_sdf_autograd(points, trans_mat, maps_cl, vols_cl, params: dict, raw: b
                               p[f"{prefix}fc_0.weight"], p[f"{prefix}fc_0.bias"], p[f"{prefix}fc_1.weight"],
                               p[f"{prefix}fc_1.bias"], p[f"{prefix}fc_2.weight"], p[f"{prefix}fc_2.bias"],
                               p[f"{prefix}fc_out.weight"], p[f"{prefix}fc_out.bias"], *vols_cl)
+
+
+def gemm_f32_tc(A: torch.Tensor, B: torch.Tensor, out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """C (M, N) (+)= A (M, K) . B (N, K)^T with fp32-level accuracy on the tensor cores (list_gemm_f32_tc); fp32, rows
+    contiguous."""
+    dev = _require_cuda(A, B)
+    M, K = A.shape
+    N = B.shape[0]
+    Cc = out if out is not None else torch.zeros(M, N, device=dev, dtype=torch.float32)
+    lo = torch.empty(M * A.stride(0) + N * B.stride(0), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _C.check(_C.lib().list_gemm_f32_tc(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), Cc.data_ptr(), Cc.stride(0),
+                                           M, N, K, int(accumulate), lo.data_ptr(), lo.numel() * 4, _stream()), "list_gemm_f32_tc")
+    return Cc
 
 
 def mlp_debug(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0):
