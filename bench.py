@@ -408,9 +408,10 @@ def main():
     if path == "lines":
         hoist_cols, k_f = state.hoist_cols, state.k_f
         k_dense = lay.k_out - hoist_cols                                       # real (unpadded) columns of the dense part
-        pair_tiles, i_chunks = (int(x) for x in stats.cpu())
+        pair_tiles, i_ksteps = (int(x) for x in stats.cpu())
+        i_chunks = i_ksteps / 4                                                # executed 16-row k-steps in units of 64-row chunks
         flop_dense = 2 * (k_dense * 512 + 512 * 256 + 256 * 256 + 256)
-        flop_interp = 2 * 512 * 64 * i_chunks * 256 / count                     # [256 x 64] x [64 x 512] per chunk and tile pair
+        flop_interp = 2 * 512 * 16 * i_ksteps * 256 / count                    # [256 x 16] x [16 x 512] per executed k-step and tile pair
         flop_exec = flop_dense + flop_interp
         hoisted_levels = [l for l in range(len(ctx.vols_cl)) if lay.vol_off[l] < hoist_cols and ctx.vol_ch[l] % 8 == 0]
         lines_touched = (begin + count - 1) // res - begin // res + 1

@@ -37,7 +37,7 @@ extern "C" {
 #define LIST_API
 #endif
 
-#define LIST_B200_ABI_VERSION 2
+#define LIST_B200_ABI_VERSION 3
 #define LIST_MAX_LEVELS 8
 #define LIST_MAX_MAPS 8
 #define LIST_NUM_DISP 7          /* reference network/modules.py:205-212 */
@@ -213,16 +213,19 @@ LIST_API int list_mlp_hoisted_trace(const ListWeights* w, int32_t hoist_cols, co
  *   list_lines_hoist_bytes size of the caller-owned buffer with the projected tensors (0: configuration not covered)
  *   list_lines_prepare     projects every image of ctx into hoist_buf
  *   list_lines_table       G[lines touched by [begin, begin+count)][rows_per_line][512] bf16 of `image`
- *   list_lines_rest        Xr[count][ldx >= k_f]: the non-hoisted feature columns (fine levels, q, zero pad)
+ *   list_lines_rest        Xr[count][ldx >= k_f]: the non-hoisted feature columns (fine levels, q, zero pad); the first three
+ *                          pad columns hold 1.0: fc_0's bias rides in the MMA (list_lines_prepare writes a copy of the
+ *                          non-hoisted weight columns with the bf16 hi / mid / lo parts of b0 in those columns)
  *   list_grid_plan         per tile of 128 consecutive steps of a z-line: the source rows its interpolation reads (rows of the
  *                          projected map and of G, as absolute addresses -- G is only used as an address here) and the <= 22
  *                          interpolation weights of every step; plan buffer >= list_grid_plan_bytes(), 256B aligned
- *   list_grid_tc_fwd       sdf[count] = MLP(Xr, interpolated hoisted terms) / out_div, from Xr and the plan (whose rows
- *                          point into hoist_buf and G: both must still be valid).  dbg_h1 (or NULL): relu(fc_0) as fp32
+ *   list_grid_tc_fwd       sdf[count] = MLP(Xr, interpolated hoisted terms) / out_div, from Xr, the plan (whose rows point
+ *                          into hoist_buf and G: both must still be valid) and hoist_buf (weight copy).  dbg_h1 (or NULL): relu(fc_0) as fp32
  *                          [count][512]; trace (or NULL): device int64[16 tiles][24] clock64() timeline of CTA 0, slots
  *                          0-11 as in list_mlp_hoisted_trace, 13 interpolation chunks issued (MMA thread), 14 plan
  *                          loaded / 15 chunks filled / 16-23 phases of its first chunk (interp warp 0); stats (or NULL):
- *                          device uint64[2], += tile pairs processed, += 64-row interpolation chunks issued */
+ *                          device uint64[2], += tile pairs processed, += 16-row k-steps of interpolation chunks issued (the padding tail
+ *                          of a tile's last 64-row chunk is skipped) */
 LIST_API int list_lines_layout(const ListCtx* ctx, const ListWeights* w, int32_t* hoist_cols, int32_t* k_f, int32_t* rows_per_line);
 LIST_API size_t list_lines_hoist_bytes(const ListCtx* ctx, const ListWeights* w);
 LIST_API int list_lines_prepare(const ListCtx* ctx, const ListWeights* w, void* hoist_buf, size_t hoist_bytes, void* stream);
@@ -235,9 +238,9 @@ LIST_API size_t list_grid_plan_bytes(int32_t res, int64_t begin, int64_t count);
 LIST_API int list_grid_plan(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t image, int32_t res,
                    double bb_min, double bb_max, int64_t begin, int64_t count, const void* G, void* plan, size_t plan_bytes,
                    void* stream);
-LIST_API int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin,
-                     int64_t count, const void* Xr, int64_t ldx, const void* plan, float* sdf, float out_div, float* dbg_h1,
-                     int64_t* trace, uint64_t* stats, void* stream);
+LIST_API int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t res, double bb_min, double bb_max,
+                     int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* plan, float* sdf, float out_div,
+                     float* dbg_h1, int64_t* trace, uint64_t* stats, void* stream);
 
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
  * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LIST_B200_LIB") or os.path.join(HERE, "liblist_b200.so")   # override: A/B builds only
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_LEVELS = 8
 MAX_MAPS = 8
 NUM_DISP = 7
@@ -88,7 +88,7 @@ SIGNATURES = {
     "list_lines_rest": (C.c_int, [_P(ListCtx), _P(ListWeights), _i32, _i32, _f64, _f64, _i64, _i64, _vp, _i64, _vp]),
     "list_grid_plan_bytes": (_sz, [_i32, _i64, _i64]),
     "list_grid_plan": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _f64, _f64, _i64, _i64, _vp, _vp, _sz, _vp]),
-    "list_grid_tc_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _vp, _i64, _vp, _vp, _f32, _vp,
+    "list_grid_tc_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _f64, _f64, _i64, _i64, _vp, _i64, _vp, _vp, _f32, _vp,
                                    _vp, _vp, _vp]),
     "list_sdf_workspace_bytes": (_sz, [_P(ListCtx), _P(ListWeights), _i64]),
     "list_sdf_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _i64, _vp, _f32, _i64, _vp, _sz, _vp]),

@@ -549,7 +549,7 @@ int list_lines_rest(const ListCtx* ctx, const ListWeights* w, int32_t image, int
                  "list_lines_rest: Xr NULL / unaligned or ldx %lld < %d", (long long)ldx, pl.k_h - 512);
   // the rest kernel addresses columns relative to a row that starts with the 512 addend columns of the round-1 layout
   return hoist::gather(ctx, w, pl, nullptr, image, res, bb_min, bb_max, begin, count, static_cast<__nv_bfloat16*>(Xr) - 512, ldx,
-                       hoist::kPartRest, static_cast<cudaStream_t>(stream));
+                       hoist::kPartRest | hoist::kPartOnes, static_cast<cudaStream_t>(stream));
 }
 
 size_t list_grid_plan_bytes(int32_t res, int64_t begin, int64_t count) {
@@ -572,15 +572,15 @@ int list_grid_plan(const ListCtx* ctx, const ListWeights* w, const void* hoist_b
   return grid_plan(ctx, pl, hoist_buf, image, res, bb_min, bb_max, begin, count, G, plan, static_cast<cudaStream_t>(stream));
 }
 
-int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count,
-                     const void* Xr, int64_t ldx, const void* plan, float* sdf, float out_div, float* dbg_h1, int64_t* trace,
-                     uint64_t* stats, void* stream) {
+int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const void* hoist_buf, int32_t res, double bb_min, double bb_max,
+                     int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* plan, float* sdf, float out_div,
+                     float* dbg_h1, int64_t* trace, uint64_t* stats, void* stream) {
   hoist::Plan pl;
   int rc = lines_plan(ctx, w, &pl, "list_grid_tc_fwd");
   if (rc) return rc;
   if ((rc = check_range(res, begin, count, "list_grid_tc_fwd"))) return rc;
-  LIST_CHECK_ARG(Xr && plan && sdf && out_div != 0.f, "list_grid_tc_fwd: NULL argument or out_div == 0");
-  return grid_tc_fwd(ctx, w, pl, res, bb_min, bb_max, begin, count, Xr, ldx, plan, sdf, out_div, dbg_h1,
+  LIST_CHECK_ARG(hoist_buf && Xr && plan && sdf && out_div != 0.f, "list_grid_tc_fwd: NULL argument or out_div == 0");
+  return grid_tc_fwd(ctx, w, pl, hoist_buf, res, bb_min, bb_max, begin, count, Xr, ldx, plan, sdf, out_div, dbg_h1,
                      reinterpret_cast<long long*>(trace), reinterpret_cast<unsigned long long*>(stats), static_cast<cudaStream_t>(stream));
 }
 
@@ -721,12 +721,12 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
             // the line tables only read the projected tensors; everything uploaded late is first read by the rest kernel
             if (i == 0 && !late_done && hooks && hooks->late && (r2 = hook_late(hooks, s))) return r2;
             return hoist::gather(ctx, w, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, static_cast<__nv_bfloat16*>(X) - 512, k_f,
-                                 hoist::kPartRest, s);
+                                 hoist::kPartRest | hoist::kPartOnes, s);
           },
           [&](int64_t i, void* X, cudaStream_t s) -> int {
             int b; int64_t n0, n;
             span(i, b, n0, n);
-            const int r2 = grid_tc_fwd(ctx, w, pl3, res, bb_min, bb_max, begin + n0, n, X, k_f, static_cast<char*>(X) + xr_bytes + g_bytes,
+            const int r2 = grid_tc_fwd(ctx, w, pl3, hbuf, res, bb_min, bb_max, begin + n0, n, X, k_f, static_cast<char*>(X) + xr_bytes + g_bytes,
                                        sdf + static_cast<int64_t>(b) * count + n0, sdf_scale, nullptr, nullptr, nullptr, s);
             return r2 ? r2 : hook_download(hooks, sdf, static_cast<int64_t>(b) * count + n0, n, s);
           });
@@ -852,10 +852,16 @@ static void plan_host(const int32_t* map_ch, const int32_t* map_in, int n_maps, 
   size_t ws = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(dtype), 256);
   if (dtype == LIST_BF16) {
     ws *= 2;                                           // double-buffered feature rows (run_chunks)
-    // hoisted-fc_0 tensors (hoist.cu): projected maps + 7 projected copies of every level with R <= 32
-    size_t h = align_up(static_cast<size_t>(B) * S * S * 512 * 2, 256) + 1024;
-    for (int l = 0; l < n_levels; ++l)
-      if (vol_res[l] <= kLinesMaxRes) h += align_up(static_cast<size_t>(7) * B * vol_res[l] * vol_res[l] * vol_res[l] * 512 * 2, 256);
+    // hoisted-fc_0 tensors (hoist.cu): the larger of the two plans, as list_sdf_workspace_bytes counts them
+    ListCtx cdim{};
+    cdim.B = B; cdim.dtype = dtype; cdim.map_size = S; cdim.map_channels = cm; cdim.n_levels = n_levels;
+    for (int l = 0; l < n_levels; ++l) { cdim.vol_res[l] = vol_res[l]; cdim.vol_ch[l] = vol_ch[l]; }
+    ListWeights wdim{};
+    wdim.dtype = LIST_BF16; wdim.k_pad = lay.k_pad; wdim.n0 = 512; wdim.n1 = 256; wdim.n2 = 256;
+    size_t h = 0;
+    hoist::Plan pl;
+    if (hoist::make_plan(&cdim, &wdim, &pl) == LIST_OK) h = align_up(pl.total, 256);
+    if (hoist::make_plan(&cdim, &wdim, &pl, kLinesLevels, kLinesMaxRes) == LIST_OK && align_up(pl.total, 256) > h) h = align_up(pl.total, 256);
     ws += h + 256;
   }
   if (dtype == LIST_F32) {                             // activations + lo copies of the fp32 MLP (mlp_f32_workspace_bytes)

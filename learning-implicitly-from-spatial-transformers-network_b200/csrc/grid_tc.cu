@@ -54,6 +54,7 @@ constexpr int UNIT_BYTES = 128 * BK * 2;           // 16 KB
 constexpr int NU = 12, NB = 12;                    // ring units / chunk barriers
 constexpr int U_FI = 3;                            // units of an F or I chunk
 constexpr int N_W = (N0 + N1) / BK;                // fc_1 + fc_2 weight chunks per tile, one unit each
+constexpr int kPre = 2;                            // I chunks whose first column half is issued under the previous tile's last epilogue
 constexpr int kIFirst = 2;                         // I chunks of EACH tile of a pair that precede the F chunks in the ring order (the rest follow them)
 constexpr int kEpiWarp0 = 2, kEpiWarps = 8, kIntWarp0 = kEpiWarp0 + kEpiWarps, kIntWarps = 4;
 constexpr int kThreads = (kIntWarp0 + kIntWarps) * 32;   // 448
@@ -70,7 +71,8 @@ constexpr uint32_t kEmpty = 0xff800000u;           // weight entry that matches 
 constexpr int kPlanRowBytes = kMaxRows * 8;        // uint64 source address per listed row
 constexpr int kPlanEntBytes = BM * kEntPad * 4;    // uint32 entries [128 steps][kEntPad]
 struct PlanBuf {
-  int* hdr;                         // [n_tiles] 64-row chunks of the tile's list (0: tile outside the launch's range)
+  int* hdr;                         // [n_tiles] 64-row chunks of the tile's list | 16-row k-steps used of the last chunk << 8
+                                    // (0: tile outside the launch's range)
   unsigned long long* rows;         // [n_tiles][kMaxRows]
   uint32_t* ent;                    // [n_tiles][128][kEntPad]
 };
@@ -120,6 +122,7 @@ struct Params {
   PlanBuf plan;
   float* dbg1;                      // optional [count][512]: relu(fc_0) in fp32 before rounding
   long long* trace;
+  int trace_stride;                 // every trace_stride-th tile pair of CTA 0 is recorded
   unsigned long long* stats;        // optional [2]: += pair tiles, += I chunks (executed-FLOP accounting of bench.py)
   uint32_t b_lbo, b_sbo, b_kadv;    // MN-major descriptor of the Brows units: bytes between 64-channel groups / 8-row groups / 16 k rows
 };
@@ -153,6 +156,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_prior1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void st_shared_zero16(uint32_t addr) {
   asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(BM) grid_plan_kernel(const Geo p, const PlanBu
   const int n_rows = nvox + npix;
   const int n_chunks = (n_rows + BK - 1) / BK;
   for (int e = n_rows + it; e < n_chunks * BK; e += BM) rows[e] = reinterpret_cast<unsigned long long>(p.zero);
-  if (it == 0) out.hdr[tile] = n_chunks;
+  if (it == 0) out.hdr[tile] = n_chunks | (((n_rows - (n_chunks - 1) * BK + 15) >> 4) << 8);
   __syncthreads();
   // ---- weight entries of this step: chunk << 23 | byte offset in the row's 128 B (16-byte pieces XOR-swizzled with the
   //      row index, as the K-major SWIZZLE_128B operand layout wants) << 16 | bf16 weight ----
@@ -344,11 +349,22 @@ __global__ void __launch_bounds__(BM) grid_plan_kernel(const Geo p, const PlanBu
     reinterpret_cast<uint4*>(ent)[i] = make_uint4(ev[4 * i], ev[4 * i + 1], ev[4 * i + 2], ev[4 * i + 3]);
 }
 
+// I chunk number ci of a tile pair in ring order -> (row list L, chunk c of that list).  Ring order: list 0 chunks [0, a0),
+// list 1 chunks [0, a1) | the F chunks | list 0 chunks [a0, nI0), list 1 chunks [a1, nI1), with a = min(n, kIFirst).
+__device__ __forceinline__ void chunk_of_seq(int ci, int nI0, int nI1, int& L, int& c) {
+  const int a0 = min(nI0, kIFirst), a1 = min(nI1, kIFirst), nIa = a0 + a1;
+  if (ci < a0) { L = 0; c = ci; }
+  else if (ci < nIa) { L = 1; c = ci - a0; }
+  else if (ci < nIa + (nI0 - a0)) { L = 0; c = ci - nIa + a0; }
+  else { L = 1; c = ci - nIa - (nI0 - a0) + a1; }
+}
+
 // ------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(kThreads, 1)
 grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW0,
                const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const Params p) {
   extern __shared__ uint8_t smem_raw[];
+  __shared__ volatile int s_flag;                    // interp warps: "the next chunk's units are already granted"
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* const gbase = smem_raw + (base - raw);
@@ -375,7 +391,8 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int n_pairs = static_cast<int>((p.n_tiles + 1) / 2);
   const int nkF = p.nkF;
   // 64-row interpolation chunks of a tile's row list (grid_plan_kernel); 0 for the tile past the end of an odd launch
-  auto chunks_of = [&](unsigned tile) -> int { return tile < p.n_tiles ? __ldg(p.plan.hdr + tile) : 0; };
+  auto hdr_of = [&](unsigned tile) -> int { return tile < p.n_tiles ? __ldg(p.plan.hdr + tile) : 0; };
+  auto chunks_of = [&](unsigned tile) -> int { return hdr_of(tile) & 0xff; };
   // I chunks of a pair as (before the F chunks) | (after them) << 16
   auto counts_of = [&](int pair) -> int {
     if (pair >= n_pairs) return 0;
@@ -387,7 +404,14 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   constexpr int kTraceTiles = 16, kTraceSlots = 24;
   const bool tracing = p.trace != nullptr && blockIdx.x == 0;
   auto stamp = [&](int tile_no, int slot) {
-    if (tracing && tile_no < kTraceTiles) p.trace[tile_no * kTraceSlots + slot] = clock64();
+    if (tracing && tile_no % p.trace_stride == 0 && tile_no / p.trace_stride < kTraceTiles) {
+      p.trace[(tile_no / p.trace_stride) * kTraceSlots + slot] = clock64();
+      if (slot == 0) {                                            // slot 17: wall clock (ns) of the same instant -> SM clock under load
+        unsigned long long ns;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+        p.trace[(tile_no / p.trace_stride) * kTraceSlots + 17] = static_cast<long long>(ns);
+      }
+    }
   };
 
   if (warp == 0 && lane == 0) {
@@ -503,34 +527,70 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         tc_fence_after();
       };
       int itn = 0;
-      unsigned long long n_chunks_i = 0;
-      int cnt = counts_of(cluster_id);
+      unsigned long long n_ksteps_i = 0;
+      int h0 = hdr_of(2u * cluster_id), h1 = hdr_of(2u * cluster_id + 1);
       for (int pair = cluster_id; pair < n_pairs; pair += num_clusters, ++itn) {
+        // ---- fc_0: D[0,512) = Aw . Brows (interpolated part, I chunks) + Xr . W0[:, hoisted..]^T (dense part, F chunks) ----
+        const int nI0 = h0 & 0xff, nI1 = h1 & 0xff, kl0 = h0 >> 8, kl1 = h1 >> 8;
+        const int nIa = min(nI0, kIFirst) + min(nI1, kIFirst), nI = nI0 + nI1;
+        // 16-row k-steps of an I chunk: the tail of a tile's last chunk holds only padding rows and is skipped
+        auto ksteps_of = [&](int ci) -> int {
+          int L, c;
+          chunk_of_seq(ci, nI0, nI1, L, c);
+          return L == 0 ? (c == nI0 - 1 ? kl0 : BK / 16) : (c == nI1 - 1 ? kl1 : BK / 16);
+        };
+        // one 256-column half j of an I chunk
+        auto issue_i_half = [&](uint32_t hd, int j, int ks, uint32_t acc) {
+          const uint64_t ad = umma_desc_sw128(unit_addr(hd));
+          const uint64_t bd = umma_desc_mn_sw128(unit_addr(hd + 1 + j), p.b_lbo, p.b_sbo);
+          for (int k = 0; k < ks; ++k)                                  // 16 k rows = 2048 B further along K
+            umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k, bd + static_cast<uint64_t>((p.b_kadv >> 4) * k), idesc_mn,
+                        acc | static_cast<uint32_t>(k != 0));
+        };
+        uint32_t acc = 0;                                             // the tile's first MMA overwrites the accumulator
+        // Column half j = 0 of the first kPre chunks is issued BEFORE the previous tile's last epilogue has drained its
+        // accumulator: that one lives in columns [256,512), and the tensor pipe executes MMAs in issue order, so the
+        // previous fc_2 has read H2 (columns [0,128)) by the time these write columns [0,256).  (Only two I chunks fit
+        // into the ring next to fc_2's weight boxes, so only two can be ready that early.)
+        const int nPre = min(nIa, kPre);
+        for (int ci = 0; ci < nPre; ++ci) {
+          const uint32_t b = (q + ci) % NB;
+          mbar_wait(ifull_bar(b), (iphase >> b) & 1u);
+          iphase ^= 1u << b;
+          tc_fence_after();
+          issue_i_half(head + U_FI * ci, 0, ksteps_of(ci), ci != 0 ? 1u : 0u);
+        }
         if (itn > 0) { mbar_wait(hready_bar, hphase); hphase ^= 1; }   // previous tile's accumulators drained
         tc_fence_after();
         stamp(itn, 0);
-        // ---- fc_0: D[0,512) = Aw . Brows (interpolated part, I chunks) + Xr . W0[:, hoisted..]^T (dense part, F chunks) ----
-        const int nIa = cnt & 0xffff, nIb = cnt >> 16;
-        n_chunks_i += static_cast<unsigned long long>(nIa + nIb);
-        uint32_t acc = 0;                                             // the tile's first MMA overwrites the accumulator
-        auto issue_i = [&](int n) {
-          for (int ci = 0; ci < n; ++ci, head += U_FI) {
+        for (int ci = 0; ci < nPre; ++ci) {
+          const int ks = ksteps_of(ci);
+          issue_i_half(head + U_FI * ci, 1, ks, ci != 0 ? 1u : 0u);
+          umma_commit<CG>(empty_bar((q + ci) % NB));
+          n_ksteps_i += static_cast<unsigned long long>(ks);
+        }
+        q += nPre;
+        head += U_FI * nPre;
+        if (nPre > 0) acc = 1;
+        auto issue_i = [&](int c0, int c1) {
+          for (int ci = c0; ci < c1; ++ci, head += U_FI) {
             wait_ifull();
+            const int ks = ksteps_of(ci);
             const uint64_t ad = umma_desc_sw128(unit_addr(head));
+            for (int k = 0; k < ks; ++k) {
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j)     // 16 k rows = 2048 B further along K
+              for (int j = 0; j < 2; ++j)
                 umma_ss<CG>(tmem_base + j * kCols, ad + 2 * k,
                             umma_desc_mn_sw128(unit_addr(head + 1 + j), p.b_lbo, p.b_sbo) + static_cast<uint64_t>((p.b_kadv >> 4) * k),
                             idesc_mn, acc | static_cast<uint32_t>(k != 0));
             }
             acc = 1;
             umma_commit<CG>(empty_bar(q % NB));
+            n_ksteps_i += static_cast<unsigned long long>(ks);
             ++q;
           }
         };
-        issue_i(nIa);
+        issue_i(nPre, nIa);
         stamp(itn, 13);
         for (int kc = 0; kc < nkF; ++kc, head += U_FI) {
           wait_full();
@@ -547,8 +607,9 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           ++q;
         }
         stamp(itn, 12);
-        issue_i(nIb);
-        cnt = counts_of(pair + num_clusters);
+        issue_i(nIa, nI);
+        h0 = hdr_of(2u * (pair + num_clusters));
+        h1 = hdr_of(2u * (pair + num_clusters) + 1);
         umma_commit<CG>(dfull_bar);
         stamp(itn, 1);
         // ---- fc_1: D[256,512) = H1(TMEM [0,256)) . W1^T ;  fc_2: D[256,512) = H2(TMEM [0,128)) . W2^T ----
@@ -573,7 +634,7 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       if (p.stats != nullptr) {
         atomicAdd(p.stats, static_cast<unsigned long long>(itn));
-        atomicAdd(p.stats + 1, n_chunks_i);
+        atomicAdd(p.stats + 1, n_ksteps_i);
       }
     }
   } else if (warp < kIntWarp0) {
@@ -599,28 +660,38 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tile_rows(p.tm, 2u * pair + rank, p.n_tiles, g0, s_lo, s_hi);
       const bool live = r_in_tile >= s_lo && r_in_tile < s_hi;
       const int64_t orow = g0 + r_in_tile - p.tm.begin;
-      // ---- after fc_0: H1 = relu(acc + b0) -> bf16 -> TMEM [0,256), compacted in place.  Step m: the pair reads accumulator
+      // ---- after fc_0: H1 = relu(acc) -> bf16 -> TMEM [0,256), compacted in place (acc includes b0).  Step m: the pair reads accumulator
       //      columns [64 m, +64) and writes H1 columns [32 m, +32); the pair barrier between the loads and the stores keeps a
       //      warp from overwriting columns its partner has not read yet (step m's stores never reach a later step's loads). ----
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(itn, 6);
+      // The loads run one step ahead of the arithmetic (two register buffers): step m + 1's columns lie beyond everything
+      // step m writes, so only the stores wait for the partner's loads.
+      {
+        uint32_t va[32], vb[32];
+        auto finish = [&](int m, uint32_t (&v)[32]) {
+          const int j = 2 * m + half;
+          uint32_t u[16];                                           // the bias came in through the MMA (Plan::bias_col)
+#pragma unroll
+          for (int i = 0; i < 16; ++i) u[i] = pack_bf16x2_relu(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          tmem_st16(tq + j * 16, u);
+          if (p.dbg1 != nullptr && live) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) p.dbg1[orow * N0 + j * 32 + i] = fmaxf(__uint_as_float(v[i]), 0.f);
+          }
+        };
+        tmem_ld32_nowait(tq + half * 32, va);
 #pragma unroll 1
-      for (int m = 0; m < N0 / 64; ++m) {
-        const int j = 2 * m + half;
-        uint32_t v[32], u[16];
-        tmem_ld32(tq + j * 32, v);
-        pair_sync();
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 bb = *reinterpret_cast<const float2*>(s_b0 + j * 32 + 2 * i);
-          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
-          u[i] = pack_bf16x2_relu(sum.x, sum.y);
-        }
-        tmem_st16(tq + j * 16, u);
-        if (p.dbg1 != nullptr && live) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) p.dbg1[orow * N0 + j * 32 + i] = fmaxf(__uint_as_float(v[i]) + s_b0[j * 32 + i], 0.f);
+        for (int m = 0; m < N0 / 64; m += 2) {
+          tmem_ld_wait32(va);
+          pair_sync();
+          tmem_ld32_nowait(tq + (2 * (m + 1) + half) * 32, vb);
+          finish(m, va);
+          tmem_ld_wait32(vb);
+          pair_sync();
+          if (m + 2 < N0 / 64) tmem_ld32_nowait(tq + (2 * (m + 2) + half) * 32, va);
+          finish(m + 1, vb);
         }
       }
       tmem_wait_st();
@@ -631,18 +702,30 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       mbar_wait_warp(dfull_bar, dphase); dphase ^= 1;
       tc_fence_after();
       if (estamp) stamp(itn, 8);
-#pragma unroll 1
-      for (int m = 0; m < N1 / 64; ++m) {
-        const int j = half * (N1 / 64) + m;
-        uint32_t v[32], u[16];
-        tmem_ld32(tq + 256 + j * 32, v);
+      {
+        uint32_t va[32], vb[32];
+        auto finish = [&](int m, uint32_t (&v)[32]) {
+          const int j = half * (N1 / 64) + m;
+          uint32_t u[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 bb = *reinterpret_cast<const float2*>(s_b1 + j * 32 + 2 * i);
-          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
-          u[i] = pack_bf16x2_relu(sum.x, sum.y);
+          for (int i = 0; i < 16; ++i) {
+            const float2 bb = *reinterpret_cast<const float2*>(s_b1 + j * 32 + 2 * i);
+            const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+            u[i] = pack_bf16x2_relu(sum.x, sum.y);
+          }
+          tmem_st16(tq + j * 16, u);
+        };
+        const uint32_t src = tq + 256 + half * (N1 / 64) * 32;
+        tmem_ld32_nowait(src, va);
+#pragma unroll 1
+        for (int m = 0; m < N1 / 64; m += 2) {
+          tmem_ld_wait32(va);
+          tmem_ld32_nowait(src + (m + 1) * 32, vb);
+          finish(m, va);
+          tmem_ld_wait32(vb);
+          if (m + 2 < N1 / 64) tmem_ld32_nowait(src + (m + 2) * 32, va);
+          finish(m + 1, vb);
         }
-        tmem_st16(tq + j * 16, u);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -653,17 +736,28 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       tc_fence_after();
       if (estamp) stamp(itn, 10);
       float2 acc2 = make_float2(0.f, 0.f);
-#pragma unroll 1
-      for (int m = 0; m < N2 / 64; ++m) {
-        const int j = half * (N2 / 64) + m;
-        uint32_t v[32];
-        tmem_ld32(tq + 256 + j * 32, v);
+      {
+        uint32_t va[32], vb[32];
+        auto finish = [&](int m, uint32_t (&v)[32]) {
+          const int j = half * (N2 / 64) + m;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float2 bb = *reinterpret_cast<const float2*>(s_b2 + j * 32 + 2 * i);
-          const float2 ww = *reinterpret_cast<const float2*>(s_w3 + j * 32 + 2 * i);
-          const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
-          acc2 = ffma2(make_float2(fmaxf(sum.x, 0.f), fmaxf(sum.y, 0.f)), ww, acc2);
+          for (int i = 0; i < 16; ++i) {
+            const float2 bb = *reinterpret_cast<const float2*>(s_b2 + j * 32 + 2 * i);
+            const float2 ww = *reinterpret_cast<const float2*>(s_w3 + j * 32 + 2 * i);
+            const float2 sum = fadd2(make_float2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1])), bb);
+            acc2 = ffma2(make_float2(fmaxf(sum.x, 0.f), fmaxf(sum.y, 0.f)), ww, acc2);
+          }
+        };
+        const uint32_t src = tq + 256 + half * (N2 / 64) * 32;
+        tmem_ld32_nowait(src, va);
+#pragma unroll 1
+        for (int m = 0; m < N2 / 64; m += 2) {
+          tmem_ld_wait32(va);
+          tmem_ld32_nowait(src + (m + 1) * 32, vb);
+          finish(m, va);
+          tmem_ld_wait32(vb);
+          if (m + 2 < N2 / 64) tmem_ld32_nowait(src + (m + 2) * 32, va);
+          finish(m + 1, vb);
         }
       }
       tc_fence_before();
@@ -707,22 +801,57 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ibar();
       if (it == 0) stamp(itn, 14);
       const int nI = nI0 + nI1;
-      const int a0 = min(nI0, kIFirst), a1 = min(nI1, kIFirst), nIa = a0 + a1;
+      const int nIa = min(nI0, kIFirst) + min(nI1, kIFirst);
+      // Chunks are filled one step ahead of their hand-over: chunk ci's row copies are in flight while chunk ci + 1 is
+      // granted, its copies issued and its weights written; only then are ci's copies awaited and ci handed to the MMA
+      // thread (the copies' L2 latency, ~1k cycles under load, is off the per-chunk critical path).  If the units of
+      // chunk ci + 1 are not free yet, chunk ci is handed over first (the ring may be waiting for exactly that chunk).
+      int pend_b = -1;
+      auto hand_over = [&](int b) {                                // this thread's copies of the chunk have landed
+        fence_proxy_async_smem();
+        ibar();                                                    // all four quarters are in place
+        if (it == 0) {
+          if (rank == 0) mbar_arrive_local(ifull_bar(b));
+          else mbar_arrive_remote(mapa(ifull_bar(b), 0));
+        }
+      };
       for (int ci = 0; ci < nI; ++ci, ++q, head += U_FI) {
         if (ci == nIa) { q += nkF; head += U_FI * nkF; }           // the pair's F chunks sit between its two groups of I chunks
         const uint32_t b = q % NB;
         const uint32_t par = (gphase >> b) & 1u;
         gphase ^= 1u << b;
-        // sequence: list 0 chunks [0, a0), list 1 chunks [0, a1) | F | list 0 chunks [a0, nI0), list 1 chunks [a1, nI1)
         int L, c;
-        if (ci < a0) { L = 0; c = ci; }
-        else if (ci < nIa) { L = 1; c = ci - a0; }
-        else if (ci < nIa + (nI0 - a0)) { L = 0; c = ci - nIa + a0; }
-        else { L = 1; c = ci - nIa - (nI0 - a0) + a1; }
+        chunk_of_seq(ci, nI0, nI1, L, c);
+        if (pend_b >= 0) {
+          if (it == 0) s_flag = mbar_test(grant_bar(b), par) ? 1 : 0;
+          ibar();
+          if (s_flag == 0) {
+            cp_async_wait_all();
+            hand_over(pend_b);
+            pend_b = -1;
+          }
+        }
         mbar_wait_warp(grant_bar(b), par);
         if (it == 0 && ci == 0) stamp(itn, 19);
         // Every chunk is filled by all four warps, a quarter of its rows each: what matters is the latency from the grant
         // to the chunk being usable, not the throughput.
+        // ---- Brows k in [16 wq, +16): this CTA's 256 channels of the listed rows, MN-major 128B-swizzled (row k of a
+        //      64-channel group at (k / 8) * 1024 + (k % 8) * 128, 16-byte piece i at (i ^ (k % 8)) * 16; groups 8 KB apart) ----
+        const uint32_t ub = unit_addr(head + 1 + bj) + static_cast<uint32_t>(bg) * 8192u + static_cast<uint32_t>(wq) * 2048u;
+        const ulonglong2* const lrows = reinterpret_cast<const ulonglong2*>(s_rows + L * kMaxRows + c * BK + wq * 16);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) {
+          const ulonglong2 rr2 = lrows[k2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const int k = 2 * k2 + u;                              // row 16 wq + k of the chunk: (k >> 3) is the 8-row group inside this quarter
+            cp_async16(ub + static_cast<uint32_t>(k >> 3) * 1024u + static_cast<uint32_t>(k & 7) * 128u +
+                           (static_cast<uint32_t>(bc ^ (k & 7)) << 4),
+                       reinterpret_cast<const __nv_bfloat16*>(u ? rr2.y : rr2.x) + col_off);
+          }
+        }
+        cp_async_commit();
+        if (it == 0 && ci == 0) stamp(itn, 20);
         // ---- Aw rows [32 wq, +32): zeros, then this CTA's weights if the list is its own tile's ----
         const uint32_t ua = unit_addr(head) + static_cast<uint32_t>(wq) * (32u * 128u);
 #pragma unroll
@@ -745,32 +874,17 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
         }
-        if (it == 0 && ci == 0) stamp(itn, 20);
-        // ---- Brows k in [16 wq, +16): this CTA's 256 channels of the listed rows, MN-major 128B-swizzled (row k of a
-        //      64-channel group at (k / 8) * 1024 + (k % 8) * 128, 16-byte piece i at (i ^ (k % 8)) * 16; groups 8 KB apart) ----
-        const uint32_t ub = unit_addr(head + 1 + bj) + static_cast<uint32_t>(bg) * 8192u + static_cast<uint32_t>(wq) * 2048u;
-        const ulonglong2* const lrows = reinterpret_cast<const ulonglong2*>(s_rows + L * kMaxRows + c * BK + wq * 16);
-#pragma unroll
-        for (int k2 = 0; k2 < 8; ++k2) {
-          const ulonglong2 rr2 = lrows[k2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const int k = 2 * k2 + u;                              // row 16 wq + k of the chunk: (k >> 3) is the 8-row group inside this quarter
-            cp_async16(ub + static_cast<uint32_t>(k >> 3) * 1024u + static_cast<uint32_t>(k & 7) * 128u +
-                           (static_cast<uint32_t>(bc ^ (k & 7)) << 4),
-                       reinterpret_cast<const __nv_bfloat16*>(u ? rr2.y : rr2.x) + col_off);
-          }
-        }
         if (it == 0 && ci == 0) stamp(itn, 21);
-        cp_async_wait_all();
-        if (it == 0 && ci == 0) stamp(itn, 22);
-        fence_proxy_async_smem();
-        ibar();                                                    // all four quarters are in place
-        if (it == 0) {
-          if (rank == 0) mbar_arrive_local(ifull_bar(b));
-          else mbar_arrive_remote(mapa(ifull_bar(b), 0));
+        if (pend_b >= 0) {
+          cp_async_wait_prior1();                                  // the previous chunk's copies (this chunk's stay in flight)
+          hand_over(pend_b);
         }
-        if (it == 0 && ci == 0) stamp(itn, 23);
+        pend_b = static_cast<int>(b);
+        if (it == 0 && ci == 0) stamp(itn, 22);
+      }
+      if (pend_b >= 0) {
+        cp_async_wait_all();
+        hand_over(pend_b);
       }
       if (nI <= nIa) { q += nkF; head += U_FI * nkF; }
       if (it == 0) stamp(itn, 15);
@@ -841,8 +955,8 @@ int grid_plan(const ListCtx* ctx, const hoist::Plan& pl, const void* hoist_buf, 
 }
 
 // Fused interpolation + MLP over grid points [begin, begin + count) of image `image` (see the header comment).
-int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, int res, double bb_min, double bb_max, int64_t begin,
-                int64_t count, const void* Xr, int64_t ldx, const void* plan_buf, float* sdf, float out_div, float* dbg1,
+int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl, const void* hoist_buf, int res, double bb_min, double bb_max,
+                int64_t begin, int64_t count, const void* Xr, int64_t ldx, const void* plan_buf, float* sdf, float out_div, float* dbg1,
                 long long* trace, unsigned long long* stats, cudaStream_t st) {
   using namespace gtc;
   if (count == 0) return LIST_OK;
@@ -862,12 +976,18 @@ int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl,
   p.plan = plan_carve(const_cast<void*>(plan_buf), p.n_tiles);
   p.dbg1 = dbg1;
   p.trace = trace;
+  {
+    const char* e = getenv("LIST_B200_TRACE_STRIDE");          // tuning aid of scripts/grid_tc_trace.py
+    const int v = e ? atoi(e) : 1;
+    p.trace_stride = v >= 1 ? v : 1;
+  }
   p.stats = stats;
   p.b_lbo = 8192; p.b_sbo = 1024; p.b_kadv = 2048;
   CUtensorMap tmX, tmW0, tmW1, tmW2;
   int rc;
   if ((rc = make_map_bf16(&tmX, Xr, static_cast<uint64_t>(k_f), static_cast<uint64_t>(count), static_cast<uint64_t>(ldx)))) return rc;
-  if ((rc = make_map_bf16(&tmW0, static_cast<const __nv_bfloat16*>(w->w0) + pl.hoist_cols, static_cast<uint64_t>(k_f), N0, w->k_pad))) return rc;
+  // fc_0's non-hoisted weight columns with b0 in the bias columns (hoist::prepare); Xr carries 1.0 there
+  if ((rc = make_map_bf16(&tmW0, static_cast<const char*>(hoist_buf) + pl.off_w0r, static_cast<uint64_t>(k_f), N0, static_cast<uint64_t>(k_f)))) return rc;
   if ((rc = make_map_bf16(&tmW1, w->w1, N0, N1, N0))) return rc;
   if ((rc = make_map_bf16(&tmW2, w->w2, N1, N2, N1))) return rc;
   int dev = 0, sms = 0;

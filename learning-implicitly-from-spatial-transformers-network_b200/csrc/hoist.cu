@@ -78,6 +78,7 @@ struct RestParams {
   int nvec;                         // 16-byte items per row of the vector levels
   int g_items;                      // phase-G items of the vector levels
   int tail0, xyz_off, k_h;          // tail region [tail0, k_h): scalar levels, q, zero pad
+  int ones;                         // 1: the three columns behind q hold 1.0 (Plan::bias_col)
   __nv_bfloat16* X;
   int64_t ldx;
   TileMap tm;
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   //      and are enumerated separately so that a warp never mixes the two kinds ----
   {
     const int ngrp = (p.k_h - p.tail0) >> 3;             // tail0 and k_h are multiples of 8
-    const int nlive = min(ngrp, (nscal + 3 + 7) >> 3);   // groups holding scalar-level or q columns
+    const int nlive = min(ngrp, (nscal + 3 + 3 * p.ones + 7) >> 3);   // groups holding scalar-level, q or bias columns
     const int ndead = ngrp - nlive;
     __nv_bfloat16* __restrict__ Xt = Xb + p.tail0;
     if (ndead > 0) {
@@ -531,6 +532,8 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         } else if (col < nscal + 3) {
           const int a = col - nscal;
           val = a == 0 ? s_q0[s] : (a == 1 ? t.qy : t.qz);
+        } else if (p.ones && col < nscal + 6) {
+          val = 1.0f;
         }
         out[j] = val;
       }
@@ -574,8 +577,30 @@ int make_plan(const ListCtx* ctx, const ListWeights* w, Plan* pl, int max_levels
     off += up(static_cast<size_t>(LIST_NUM_DISP) * ctx->B * R * R * R * kN0 * 2);
   }
   pl->off_zero = off; off += up(kN0 * 2);                                  // one all-zero row (padding rows of grid_tc.cu)
+  pl->off_w0r = off; off += up(static_cast<size_t>(kN0) * (lay.k_pad - cols) * 2);
+  pl->bias_col = lay.xyz_off + 3 - cols;
+  if (pl->bias_col + 3 > lay.k_pad - cols) return LIST_ENOSYS;            // no pad columns left for the bias
   pl->total = off;
   return LIST_OK;
+}
+
+// W0r[n][c] = W0[n][hoist_cols + c], with the bf16 hi / mid / lo parts of b0[n] in columns [bias_col, +3).
+__global__ void w0r_kernel(const __nv_bfloat16* __restrict__ w0, int k_pad, int hoist_cols, int k_f, int bias_col,
+                           const float* __restrict__ b0, __nv_bfloat16* __restrict__ w0r) {
+  const int n = blockIdx.x;
+  for (int c = threadIdx.x; c < k_f; c += blockDim.x) {
+    __nv_bfloat16 v = w0[static_cast<size_t>(n) * k_pad + hoist_cols + c];
+    if (c >= bias_col && c < bias_col + 3) {
+      float r = b0[n];
+      __nv_bfloat16 part = __float2bfloat16_rn(r);
+      for (int i = 0; i < c - bias_col; ++i) {
+        r -= __bfloat162float(part);
+        part = __float2bfloat16_rn(r);
+      }
+      v = part;
+    }
+    w0r[static_cast<size_t>(n) * k_f + c] = v;
+  }
 }
 
 // Projects the maps and the hoisted levels of every image through their W0 blocks.
@@ -596,6 +621,9 @@ int prepare(const ListCtx* ctx, const ListWeights* w, const Plan& pl, void* buf,
       return rc;
   }
   LIST_CUDA(cudaMemsetAsync(base + pl.off_zero, 0, kN0 * 2, st));
+  w0r_kernel<<<kN0, 128, 0, st>>>(static_cast<const __nv_bfloat16*>(w->w0), w->k_pad, pl.hoist_cols, pl.k_h - kN0, pl.bias_col, w->b0,
+                                  reinterpret_cast<__nv_bfloat16*>(base + pl.off_w0r));
+  LIST_LAUNCH_CHECK("w0r_kernel");
   return LIST_OK;
 }
 
@@ -742,6 +770,7 @@ int gather(const ListCtx* ctx, const ListWeights* w, const Plan& pl, const void*
   if (rc2) return rc2;
   r.X = a.X;
   r.ldx = ldx;
+  r.ones = (parts & kPartOnes) ? 1 : 0;
   fill_tilemap(&r.tm, res, bb_min, bb_max, begin, count, r.tm.kPz);
 
   static const int vec = []() { const char* e = getenv("LIST_B200_HOIST_VEC"); return (e && e[0] == '8') ? 8 : 4; }();

@@ -320,7 +320,8 @@ class LineTableState:
 
     def rest(self, image: int, res: int, begin: int, count: int, bb_min: float = -0.5, bb_max: float = 0.5,
              out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Xr (count, k_f) bf16: the feature columns that are not hoisted."""
+        """Xr (count, k_f) bf16: the feature columns that are not hoisted (plus 1.0 in the three pad columns behind q,
+        through which fc_0's bias enters the MMA)."""
         X = out if out is not None else torch.empty(count, self.k_f, device=self.dev, dtype=torch.bfloat16)
         cs, ws = self.ctx.struct(), self.base.struct()
         with torch.cuda.device(self.dev):
@@ -344,14 +345,14 @@ class LineTableState:
                  bb_min: float = -0.5, bb_max: float = 0.5, debug: bool = False, trace: bool = False,
                  stats: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
         """Fused interpolation + MLP.  Returns sdf (count,) [, relu(fc_0) (count, 512) fp32] [, trace (16, 24) int64].
-        stats: optional device int64[2] accumulating (tile pairs, interpolation chunks).  The G tensor the plan was built
+        stats: optional device int64[2] accumulating (tile pairs, executed 16-row k-steps of interpolation chunks).  The G tensor the plan was built
         for must still be alive."""
         sdf = out if out is not None else torch.empty(count, device=self.dev, dtype=torch.float32)
         h1 = torch.zeros(count, 512, device=self.dev, dtype=torch.float32) if debug else None
         tr = torch.zeros(16, 24, device=self.dev, dtype=torch.int64) if trace else None
         cs, ws = self.ctx.struct(), self.base.struct()
         with torch.cuda.device(self.dev):
-            _C.check(_C.lib().list_grid_tc_fwd(C.byref(cs), C.byref(ws), res, bb_min, bb_max, begin, count,
+            _C.check(_C.lib().list_grid_tc_fwd(C.byref(cs), C.byref(ws), self.buf.data_ptr(), res, bb_min, bb_max, begin, count,
                                                Xr.data_ptr(), Xr.stride(0), plan.data_ptr(), sdf.data_ptr(), float(out_div),
                                                None if h1 is None else h1.data_ptr(), None if tr is None else tr.data_ptr(),
                                                None if stats is None else stats.data_ptr(), _stream()), "list_grid_tc_fwd")

@@ -39,21 +39,25 @@ def main():
         ev[4].record()
         torch.cuda.synchronize()
     t = [ev[i].elapsed_time(ev[i + 1]) for i in range(4)]
-    pairs, chunks = (int(x) for x in stats.cpu())
+    pairs, ksteps = (int(x) for x in stats.cpu())
+    chunks = ksteps / 4
     print(f"res {res} rows {rows} T={trans}: lines {t[0]:.3f} ms, rest {t[1]:.3f} ms, plan {t[2]:.3f} ms, grid_tc {t[3]:.3f} ms "
           f"({rows / t[3] / 1e3:.1f} M rows/s); {chunks / max(pairs, 1):.2f} interpolation chunks per tile pair")
     tr = tr.cpu().numpy().astype(np.float64)
     names = ["start", "fc0 issued", "fc1 start", "fc1 issued", "fc2 start", "fc2 issued", "fc0 done", "ep0 done", "fc1 done",
              "ep1 done", "fc2 done", "ep2 done", "-", "I issued", "plan loaded", "I filled",
-             "loop top", "ibar done", "plan0 done", "grant c0", "A done", "cp issued", "cp landed", "arrived"]
+             "loop top", "wall ns", "plan0 done", "grant c0", "A done", "cp issued", "cp landed", "arrived"]
     t0 = tr[:, 0:1]
     rel = tr - t0
     np.set_printoptions(linewidth=200, suppress=True)
-    print("cycles relative to the tile's start (rows = tiles 2..9 of CTA 0):")
+    print("cycles relative to the tile's start (rows = recorded tiles 2..15 of CTA 0):")
     print("  " + "  ".join(f"{n:>10s}" for n in names))
-    for i in range(2, 10):
+    for i in range(2, 16):
         print("  " + "  ".join(f"{rel[i, j]:10.0f}" for j in range(len(names))))
-    print("tile period (cycles):", np.diff(tr[2:12, 0]))
+    stride = int(os.environ.get("LIST_B200_TRACE_STRIDE", "1"))
+    dcyc, dns = tr[15, 0] - tr[2, 0], tr[15, 17] - tr[2, 17]
+    print(f"SM clock under load (clock64 / globaltimer between recorded tiles 2 and 15): {dcyc / max(dns, 1):.3f} GHz")
+    print("tile period (cycles):", np.diff(tr[2:16, 0]) / stride)
 
 
 if __name__ == "__main__":

@@ -100,14 +100,18 @@ def test_stages_against_the_oracle_and_the_unhoisted_rows(size, res, begin, coun
     G = ls.table(0, res, begin, count)
     Xr = ls.rest(0, res, begin, count)
     Xfull = hotpath.gather_grid_features(ctx, 0, res, begin, count)
-    assert torch.equal(Xr, Xfull[:, ls.hoist_cols:ls.hoist_cols + ls.k_f])
+    expect = Xfull[:, ls.hoist_cols:ls.hoist_cols + ls.k_f].clone()
+    bias_col = ctx.layout.xyz_off + 3 - ls.hoist_cols                  # fc_0's bias rides in the MMA: 1.0 in three pad columns
+    expect[:, bias_col:bias_col + 3] = 1.0
+    assert torch.equal(Xr, expect)
     plan = ls.plan(0, res, begin, count, G)
     stats = torch.zeros(2, device=DEV, dtype=torch.int64)
     sdf, h1 = ls.evaluate(res, begin, count, Xr, plan, 1.0, debug=True, stats=stats)
     h1_ref = torch.relu(Xfull.float() @ kw.w0.float().t() + kw.b0)
     dh = (h1 - h1_ref).abs().max().item()
     err = (sdf.cpu() - ref).abs().max().item()
-    pairs, chunks = (int(x) for x in stats.cpu())
+    pairs, ksteps = (int(x) for x in stats.cpu())
+    chunks = ksteps / 4
     print(f"{size} res {res} T={trans}: relu(fc_0) max|d| {dh:.3e}, sdf max|d| {err:.3e}, {chunks / max(pairs, 1):.2f} interpolation chunks per tile pair")
     assert torch.isfinite(sdf).all()
     assert dh <= 3e-2 and err <= BF16_TOL
