@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_build")
 LIB = os.path.join(HERE, "liblist_b200.so")
-SOURCES = ["api.cu", "prep.cu", "gather.cu", "gather_grid.cu", "gather_bwd.cu", "mlp_f32.cu", "tgemm.cu", "mlp_tc.cu", "hoist.cu", "lines.cu", "grid_tc.cu", "mcubes.cu"]
+SOURCES = ["api.cu", "prep.cu", "gather.cu", "gather_grid.cu", "gather_bwd.cu", "mlp_f32.cu", "tgemm.cu", "mlp_tc.cu", "hoist.cu", "lines.cu", "lines_tc.cu", "grid_tc.cu", "mcubes.cu"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",

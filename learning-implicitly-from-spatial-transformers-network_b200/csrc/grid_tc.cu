@@ -139,19 +139,6 @@ __device__ __forceinline__ void tile_rows(const TileMap& m, unsigned tile, unsig
   if (s_hi < s_lo) s_hi = s_lo;
 }
 
-// UMMA shared-memory descriptor of an MN-major operand, 128B swizzle (cute: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
-// units): a k row is 64 elements = 128 B, 8 k rows form a 1024 B swizzle atom, SBO = bytes between 8-row groups along K,
-// LBO = bytes between 64-element groups along N.
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-  d |= static_cast<uint64_t>(lbo >> 4) << 16;
-  d |= static_cast<uint64_t>(sbo >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version 1 (sm_100)
-  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
-  return d;
-}
-
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src));
 }

@@ -16,6 +16,8 @@
 // voxel cell of the finest hoisted level, so per displacement the lines read the same 3 (H) x 2 (D) projected rows; those
 // are loaded and reduced along D once, and every line takes its H-interpolation from the 3 reduced rows.  That cuts the
 // L2 -> SM traffic of the naive per-line form (28 row reads per table row and line) by ~5x and leaves an FMA-bound kernel.
+#include <cstdlib>
+
 #include "grid_common.cuh"
 #include "hoist.cuh"
 
@@ -183,9 +185,20 @@ size_t lines_bytes(const Plan& pl, int res, int64_t begin, int64_t count) {
   return static_cast<size_t>(nlines) * pl.rpl * kN0L * 2;
 }
 
+int lines_tc(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max, int64_t begin,
+             int64_t count, void* G, cudaStream_t st);   // lines_tc.cu
+
 int lines(const ListCtx* ctx, const Plan& pl, const void* buf, int image, int res, double bb_min, double bb_max, int64_t begin,
           int64_t count, void* G, cudaStream_t st) {
   if (count == 0 || pl.nh == 0) return LIST_OK;
+  // LIST_B200_LINES_TC=1: the tensor-core formulation (lines_tc.cu).  Correct, but measured slower than this file's SIMT
+  // kernel on B200 (1.38 vs 1.35 ms per 4 M rows at 256^3, 1.5 vs 0.86 ms at 128^3: its pipeline skeleton alone takes
+  // 0.7 ms), so it is opt-in; DESIGN.md section 4.4.
+  const char* e = getenv("LIST_B200_LINES_TC");
+  if (e && e[0] == '1') {
+    const int rc = lines_tc(ctx, pl, buf, image, res, bb_min, bb_max, begin, count, G, st);
+    if (rc != LIST_ENOSYS) return rc;
+  }
   const char* base = static_cast<const char*>(buf);
   LinesParams p{};
   p.nh = pl.nh;

@@ -138,6 +138,19 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
   return d;
 }
+// UMMA shared-memory descriptor of an MN-major operand, 128B swizzle (cute: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte
+// units): a k row is 64 elements = 128 B, 8 k rows form a 1024 B swizzle atom, SBO = bytes between 8-row groups along K,
+// LBO = bytes between 64-element groups along N.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;                        // descriptor version 1 (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;                        // SWIZZLE_128B
+  return d;
+}
+
 // Instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29).
 __host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |

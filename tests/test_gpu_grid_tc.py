@@ -151,3 +151,21 @@ def test_zero_weights_give_the_bias_chain():
     h = torch.relu(bf(w["fc.fc_2.weight"].squeeze(-1)) @ h + w["fc.fc_2.bias"])
     want = (w["fc.fc_out.weight"].squeeze(-1) @ h + w["fc.fc_out.bias"]).item()
     assert (got - want).abs().max().item() <= 1e-5
+
+
+@pytest.mark.parametrize("size,res,begin,count", [("small", 40, 12345, 20000), ("full", 128, 128 * 128 * 37 + 128 * 5 + 37, 70000),
+                                                  ("full", 256, 256 * 256 * 100 + 256 * 31, 256 * 300)])
+def test_tensor_core_line_tables_match_the_simt_kernel(monkeypatch, size, res, begin, count):
+    """lines_tc.cu (opt-in, LIST_B200_LINES_TC=1): the H interpolation of the tables as a GEMM on the tensor cores with TMA
+    tensor stores, against lines.cu's SIMT kernel.  One more bf16 rounding (the D-reduced rows) plus bf16 H weights."""
+    inp, g, ctx, kw = _setup(37, size, "camera")
+    ls = hotpath.LineTableState(ctx, kw)
+    monkeypatch.delenv("LIST_B200_LINES_TC", raising=False)
+    G0 = ls.table(0, res, begin, count)
+    monkeypatch.setenv("LIST_B200_LINES_TC", "1")
+    G1 = ls.table(0, res, begin, count)
+    torch.cuda.synchronize()
+    scale = G0.float().abs().max().item()
+    err = (G1.float() - G0.float()).abs().max().item()
+    print(f"{size} res {res}: max|dG| {err:.3e} of {scale:.3f}")
+    assert err <= 1.2e-2 * max(scale, 1.0)
