@@ -69,6 +69,9 @@ struct RestParams {
   int R[kRestLevels], C[kRestLevels], xoff[kRestLevels];   // xoff: first column of the level in the hoisted row
   int cells_max[kRestLevels];       // table rows per (level, displacement)
   int toff[kRestLevels];            // first float of the level's tables in shared memory
+  int dstr[kRestLevels];            // floats between the tables of consecutive displacements: cells_max * C plus 4 floats of
+                                    // padding for the vector levels, so that the 16-byte accesses of the lanes of a warp (one
+                                    // per (displacement, channel vector)) spread over the banks instead of hitting the same ones
   int tab_floats;                   // floats of all column tables (the per-step tables follow)
   int nvl, nsl;                     // vector levels [0, nvl), scalar levels [nvl, nvl + nsl)
   int lwarp0[kRestLevels + 1];      // phase L: warps [lwarp0[i], lwarp0[i+1]) work on vector level i
@@ -377,7 +380,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       const int rel = col - p.xoff[li];
       if (rel >= 0 && rel < LIST_NUM_DISP * p.C[li]) {
         const int d = rel / p.C[li], c = rel % p.C[li];
-        val = (p.toff[li] + d * p.cells_max[li] * p.C[li] + c) | ((li * 3 + shift_class(d)) << 24);
+        val = (p.toff[li] + d * p.dstr[li] + c) | ((li * 3 + shift_class(d)) << 24);
       }
     }
     s_tailtab[j] = val;
@@ -412,18 +415,40 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       const Corner c0 = cor[0], c1 = cor[1], c2 = cor[2], c3 = cor[3];
       const int ncell = s_ncell[li][cls];
       const __nv_bfloat16* __restrict__ src = p.vols[li] + static_cast<uint32_t>(s_first[li][cls] + lane0) * C + cvv * 8;
-      float* __restrict__ dstt = s_tab + p.toff[li] + (d * cm + lane0) * C + cvv * 8;
+      float* __restrict__ dstt = s_tab + p.toff[li] + d * p.dstr[li] + lane0 * C + cvv * 8;
       const int sstep = lanes * C;
-      for (int c = lane0; c < ncell; c += lanes, src += sstep, dstt += sstep) {
-        float v0[8], v1[8], v2[8], v3[8], g[8];
-        load8(src + c0.base, v0);
-        load8(src + c1.base, v1);
-        load8(src + c2.base, v2);
-        load8(src + c3.base, v3);
+      // the four corner loads of the next cell are issued before this cell's arithmetic (two register sets)
+      auto issue = [&](const __nv_bfloat16* sp, uint4 (&r)[4]) {
+        r[0] = __ldg(reinterpret_cast<const uint4*>(sp + c0.base));
+        r[1] = __ldg(reinterpret_cast<const uint4*>(sp + c1.base));
+        r[2] = __ldg(reinterpret_cast<const uint4*>(sp + c2.base));
+        r[3] = __ldg(reinterpret_cast<const uint4*>(sp + c3.base));
+      };
+      auto work = [&](const uint4 (&r)[4], float* dp) {
+        const uint32_t w0[4] = {r[0].x, r[0].y, r[0].z, r[0].w}, w1[4] = {r[1].x, r[1].y, r[1].z, r[1].w};
+        const uint32_t w2[4] = {r[2].x, r[2].y, r[2].z, r[2].w}, w3[4] = {r[3].x, r[3].y, r[3].z, r[3].w};
+        float g[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) g[j] = fmaf(v3[j], c3.w, fmaf(v2[j], c2.w, fmaf(v1[j], c1.w, v0[j] * c0.w)));
-        *reinterpret_cast<float4*>(dstt) = make_float4(g[0], g[1], g[2], g[3]);
-        *reinterpret_cast<float4*>(dstt + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        for (int j = 0; j < 4; ++j) {
+          const float2 e0 = bf16x2_to_f2(w0[j]), e1 = bf16x2_to_f2(w1[j]), e2 = bf16x2_to_f2(w2[j]), e3 = bf16x2_to_f2(w3[j]);
+          g[2 * j] = fmaf(e3.x, c3.w, fmaf(e2.x, c2.w, fmaf(e1.x, c1.w, e0.x * c0.w)));
+          g[2 * j + 1] = fmaf(e3.y, c3.w, fmaf(e2.y, c2.w, fmaf(e1.y, c1.w, e0.y * c0.w)));
+        }
+        *reinterpret_cast<float4*>(dp) = make_float4(g[0], g[1], g[2], g[3]);
+        *reinterpret_cast<float4*>(dp + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      };
+      uint4 ra[4], rb[4];
+      int c = lane0;
+      if (c < ncell) issue(src, ra);
+#pragma unroll 1
+      while (c < ncell) {
+        if (c + lanes < ncell) issue(src + sstep, rb);
+        work(ra, dstt);
+        c += lanes; src += sstep; dstt += sstep;
+        if (c >= ncell) break;
+        if (c + lanes < ncell) issue(src + sstep, ra);
+        work(rb, dstt);
+        c += lanes; src += sstep; dstt += sstep;
       }
     }
     // scalar levels (C % 8 != 0): one (displacement, cell, channel) value per item
@@ -444,7 +469,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         float r = __bfloat162float(src[cor[0].base]) * cor[0].w;
 #pragma unroll
         for (int k = 1; k < 4; ++k) r = fmaf(__bfloat162float(src[cor[k].base]), cor[k].w, r);
-        s_tab[p.toff[li] + (d * cm + c) * C + ch] = r;
+        s_tab[p.toff[li] + d * p.dstr[li] + c * C + ch] = r;
       }
     }
   }
@@ -472,7 +497,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       const unsigned char* __restrict__ rels = s_rel + (li * 3 + cls) * kPz + t.s_lo;
       const float* __restrict__ w1s = s_w1 + (li * 3 + cls) * kPz + t.s_lo;
       const int last = s_ncell[li][cls] - 1;
-      const float* __restrict__ tab = s_tab + p.toff[li] + d * cm * C + cvv * 8;
+      const float* __restrict__ tab = s_tab + p.toff[li] + d * p.dstr[li] + cvv * 8;
       float G0[8], Dv[8];
       int cc = -1;
       __nv_bfloat16* __restrict__ dst = Xb + static_cast<int64_t>(sr0) * p.ldx + p.xoff[li] + d * C + cvv * 8;
@@ -704,7 +729,8 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       if (cm > r.R[i]) cm = r.R[i];
       r.cells_max[i] = cm;
       r.toff[i] = static_cast<int>(floats);
-      floats += static_cast<size_t>(LIST_NUM_DISP) * cm * r.C[i];
+      r.dstr[i] = cm * r.C[i] + (i < r.nvl ? 4 : 0);
+      floats += static_cast<size_t>(LIST_NUM_DISP) * r.dstr[i];
       if (i < r.nvl) items += LIST_NUM_DISP * cm * (r.C[i] / 8);
     }
     static const size_t budget = []() {                // LIST_B200_REST_SMEM_KB: table budget per CTA (tuning aid)

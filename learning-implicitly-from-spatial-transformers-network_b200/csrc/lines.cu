@@ -118,63 +118,95 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
   if (jlo >= jhi) return;
   const int64_t out_line0 = lz * res + ly0 - p.line_first;       // may be negative for the lines below jlo
   const int v = tid & 127, ig = tid >> 7;                        // 4-channel vector, node group
+  // Steps of a thread: (node i, displacement in class order 0 3 4 5 6 | 1 | 2).  The six row loads of step n + 1 are issued
+  // before step n's arithmetic (two register sets, the loop is unrolled by two), so the loads' latency -- the kernel's
+  // dominant stall at 16 warps per SM -- hides behind ~100 FMAs; a class's rows are stored when its last step is done.
   for (int h = 0; h < p.nh; ++h) {
     const int R = p.R[h];
     const __nv_bfloat16* __restrict__ pv = p.pvol[h] + v * 4;
     const uint32_t ds = p.dstride[h];
-    for (int i = ig; i < R; i += kLinesThreads / 128) {
-      const uint32_t ioff = static_cast<uint32_t>(i) * kN0L;
-#pragma unroll 1
-      for (int cls = 0; cls < 3; ++cls) {
-        float acc[LY][4];
+    if (ig >= R) continue;
+    float2 acc[LY][2];
+    auto issue = [&](int i, int sq, uint2 (&r0)[kNY], uint2 (&r1)[kNY]) {
+      const int d = sq == 0 ? 0 : (sq < 5 ? sq + 2 : sq - 4);
+      const DispGeo& g = s_geo[h][d];
+      const __nv_bfloat16* __restrict__ pd = pv + static_cast<size_t>(d) * ds + static_cast<uint32_t>(i) * kN0L;
+      const bool two = s_wy[h][d][0][3] != 0.f;                   // uniform over the CTA
 #pragma unroll
-        for (int j = 0; j < LY; ++j)
-#pragma unroll
-          for (int c = 0; c < 4; ++c) acc[j][c] = 0.f;
-        const int nd = cls == 0 ? 5 : 1;
-#pragma unroll 1
-        for (int di = 0; di < nd; ++di) {
-          const int d = cls == 0 ? (di == 0 ? 0 : di + 2) : cls;
-          const DispGeo& g = s_geo[h][d];
-          const __nv_bfloat16* __restrict__ pd = pv + static_cast<size_t>(d) * ds + ioff;
-          const bool two = s_wy[h][d][0][3] != 0.f;                 // uniform over the CTA
-          float u[kNY][4];
-          {
-            float t0[kNY][4], t1[kNY][4];
-#pragma unroll
-            for (int k = 0; k < kNY; ++k) {
-              if (k < 2 || !two) {
-                const uint32_t yo = static_cast<uint32_t>(g.yn[k]) * R * kN0L;
-                load4(pd + g.z0 + yo, t0[k]);
-                load4(pd + g.z1 + yo, t1[k]);
-              }
-            }
-#pragma unroll
-            for (int k = 0; k < kNY; ++k)
-#pragma unroll
-              for (int c = 0; c < 4; ++c) u[k][c] = (k < 2 || !two) ? fmaf(t1[k][c], g.wz1, t0[k][c] * g.wz0) : 0.f;
-          }
-          if (two) {
-#pragma unroll
-            for (int j = 0; j < LY; ++j) {
-              const float2 w = *reinterpret_cast<const float2*>(s_wy[h][d][j]);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(u[1][c], w.y, fmaf(u[0][c], w.x, acc[j][c]));
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < LY; ++j) {
-              const float4 w = *reinterpret_cast<const float4*>(s_wy[h][d][j]);
-#pragma unroll
-              for (int c = 0; c < 4; ++c) acc[j][c] = fmaf(u[2][c], w.z, fmaf(u[1][c], w.y, fmaf(u[0][c], w.x, acc[j][c])));
-            }
-          }
+      for (int k = 0; k < kNY; ++k) {
+        if (k < 2 || !two) {
+          const uint32_t yo = static_cast<uint32_t>(g.yn[k]) * R * kN0L;
+          r0[k] = __ldg(reinterpret_cast<const uint2*>(pd + g.z0 + yo));
+          r1[k] = __ldg(reinterpret_cast<const uint2*>(pd + g.z1 + yo));
         }
+      }
+    };
+    auto work = [&](int i, int sq, const uint2 (&r0)[kNY], const uint2 (&r1)[kNY]) {
+      const int d = sq == 0 ? 0 : (sq < 5 ? sq + 2 : sq - 4);
+      const DispGeo& g = s_geo[h][d];
+      const bool two = s_wy[h][d][0][3] != 0.f;
+      if (sq == 0 || sq >= 5) {
+#pragma unroll
+        for (int j = 0; j < LY; ++j) { acc[j][0] = make_float2(0.f, 0.f); acc[j][1] = make_float2(0.f, 0.f); }
+      }
+      float2 u[kNY][2];
+      const float2 wz0 = make_float2(g.wz0, g.wz0), wz1 = make_float2(g.wz1, g.wz1);
+#pragma unroll
+      for (int k = 0; k < kNY; ++k) {
+        if (k < 2 || !two) {
+          const float2 a0 = bf16x2_to_f2(r0[k].x), a1 = bf16x2_to_f2(r0[k].y), b0 = bf16x2_to_f2(r1[k].x), b1 = bf16x2_to_f2(r1[k].y);
+          u[k][0] = ffma2(b0, wz1, make_float2(a0.x * g.wz0, a0.y * g.wz0));
+          u[k][1] = ffma2(b1, wz1, make_float2(a1.x * g.wz0, a1.y * g.wz0));
+        } else {
+          u[k][0] = make_float2(0.f, 0.f); u[k][1] = make_float2(0.f, 0.f);
+        }
+      }
+      if (two) {
+#pragma unroll
+        for (int j = 0; j < LY; ++j) {
+          const float2 w = *reinterpret_cast<const float2*>(s_wy[h][d][j]);
+          const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) acc[j][c] = ffma2(u[1][c], wy, ffma2(u[0][c], wx, acc[j][c]));
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < LY; ++j) {
+          const float4 w = *reinterpret_cast<const float4*>(s_wy[h][d][j]);
+          const float2 wx = make_float2(w.x, w.x), wy = make_float2(w.y, w.y), wz = make_float2(w.z, w.z);
+#pragma unroll
+          for (int c = 0; c < 2; ++c) acc[j][c] = ffma2(u[2][c], wz, ffma2(u[1][c], wy, ffma2(u[0][c], wx, acc[j][c])));
+        }
+      }
+      if (sq >= 4) {                                                // last displacement of its class
+        const int cls = sq - 4;
         const size_t row = static_cast<size_t>(p.rowbase[h] + cls * R + i);
 #pragma unroll
         for (int j = 0; j < LY; ++j)
-          if (j >= jlo && j < jhi) store4(p.G + (static_cast<size_t>(out_line0 + j) * p.rpl + row) * kN0L + v * 4, acc[j]);
+          if (j >= jlo && j < jhi) {
+            uint2 o;
+            o.x = pack_bf16x2(acc[j][0].x, acc[j][0].y);
+            o.y = pack_bf16x2(acc[j][1].x, acc[j][1].y);
+            *reinterpret_cast<uint2*>(p.G + (static_cast<size_t>(out_line0 + j) * p.rpl + row) * kN0L + v * 4) = o;
+          }
       }
+    };
+    uint2 a0[kNY], a1[kNY], b0[kNY], b1[kNY];
+    int i = ig, sq = 0;
+    issue(i, sq, a0, a1);
+#pragma unroll 1
+    while (i < R) {
+      int ni = i, ns = sq + 1;
+      if (ns == LIST_NUM_DISP) { ns = 0; ni = i + kLinesThreads / 128; }
+      if (ni < R) issue(ni, ns, b0, b1);
+      work(i, sq, a0, a1);
+      i = ni; sq = ns;
+      if (i >= R) break;
+      ni = i; ns = sq + 1;
+      if (ns == LIST_NUM_DISP) { ns = 0; ni = i + kLinesThreads / 128; }
+      if (ni < R) issue(ni, ns, a0, a1);
+      work(i, sq, b0, b1);
+      i = ni; sq = ns;
     }
   }
 }
