@@ -79,3 +79,58 @@ def test_gpu_generate_mesh_matches_reference_recipe(tmp_path):
     assert np.abs(np.asarray(mesh.vertices) - v_ref).max() <= 1e-6 and np.array_equal(np.asarray(mesh.faces), t_ref)
     mesh.export(str(tmp_path / "m.obj"))
     assert (tmp_path / "m.obj").stat().st_size > 1000
+
+
+def two_balls_and_torus_sdf(n):
+    ax = np.linspace(-0.5, 0.5, n)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    torus = np.sqrt((np.sqrt(X ** 2 + Y ** 2) - 0.3) ** 2 + Z ** 2) - 0.1
+    b1 = np.sqrt((X - 0.25) ** 2 + (Y + 0.2) ** 2 + (Z - 0.33) ** 2) - 0.11
+    b2 = np.sqrt((X + 0.3) ** 2 + (Y - 0.3) ** 2 + (Z + 0.3) ** 2) - 0.13
+    return np.minimum(np.minimum(torus, b1), b2).astype(np.float32)
+
+
+def _compare_with_marching_tets(u, verts, tris, smooth, vol_tol):
+    """Bounds a marching-cubes mesh by the table-free marching-tetrahedra surface of the same grid (oracle/mtets_oracle.py):
+    identical vertex set on the grid edges, same orientation, volume within vol_tol; for shapes the grid resolves also the
+    same Euler characteristic and the same area within 1 %."""
+    from oracle import mtets_oracle as T
+    v2, t2, on_axis = T.marching_tets(u, 0.0)
+    chi2, boundary2, nonmanifold2, vol2, area2 = M.mesh_invariants(v2, t2)
+    chi, boundary, nonmanifold, vol, area = M.mesh_invariants(np.asarray(verts), np.asarray(tris))
+    assert boundary2 == 0 and boundary == 0
+    a = np.asarray(verts, dtype=np.float32)
+    b = v2[on_axis]
+    assert len(a) == len(b)
+    assert np.array_equal(a[np.lexsort(a.T[::-1])], b[np.lexsort(b.T[::-1])])    # bit-identical vertex sets
+    assert vol * vol2 > 0 and abs(vol - vol2) <= vol_tol * abs(vol2)
+    if smooth:
+        assert (nonmanifold, nonmanifold2) == (0, 0) and chi == chi2
+        assert abs(area - area2) <= 0.01 * area2
+    return chi, vol, vol2
+
+
+@pytest.mark.parametrize("name,n,chi_expected", [("sphere", 40, 2), ("torus_balls", 48, 4)])
+def test_oracle_agrees_with_marching_tetrahedra(name, n, chi_expected):
+    """Second, independent extractor (no case table at all): pins what can be pinned of the marching-cubes step without
+    PyMCubes -- vertex set, orientation, topology and enclosed volume."""
+    u = -(sphere_sdf(n) if name == "sphere" else two_balls_and_torus_sdf(n))
+    v, t = M.marching_cubes(u, 0.0)
+    chi, vol, vol2 = _compare_with_marching_tets(u, v, t, smooth=True, vol_tol=5e-3)
+    assert chi == chi_expected                                      # sphere: 2; torus (0) + two balls (2 + 2)
+    # ambiguous faces everywhere (noise at the cell scale): the surfaces differ inside cells, the volume still agrees
+    u = -bumpy_sdf(32)
+    v, t = M.marching_cubes(u, 0.0)
+    _compare_with_marching_tets(u, v, t, smooth=False, vol_tol=1e-2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["torus_balls", "bumpy"])
+def test_gpu_marching_cubes_against_marching_tetrahedra(kind):
+    from list_b200 import hotpath
+    n = 48 if kind == "torus_balls" else 32
+    u = -(two_balls_and_torus_sdf(n) if kind == "torus_balls" else bumpy_sdf(n))
+    verts, tris = hotpath.marching_cubes(torch.from_numpy(u).cuda(), 0.0)
+    torch.cuda.synchronize()
+    _compare_with_marching_tets(u, verts.cpu().numpy(), tris.cpu().numpy(), smooth=(kind == "torus_balls"),
+                                vol_tol=5e-3 if kind == "torus_balls" else 1e-2)
