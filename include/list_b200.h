@@ -131,6 +131,15 @@ LIST_API int list_prep_maps(const float* const* maps_nchw, const int32_t* ch, co
 LIST_API int list_prep_volume(const float* vol_ncdhw, int32_t B, int32_t C, int32_t R, void* out,
                      int32_t dtype, void* stream);
 
+/* a-9, adjoints of the two layout steps (autograd of reference modules.py:25-35 and of the voxel-encoder outputs feeding
+ * modules.py:264-265), fp32: the channels-last gradients list_sdf_bwd produces -> gradients in the reference layout.
+ *   list_prep_maps_bwd    g [B][S][S][sum ch] -> grads_nchw[i] [B][ch[i]][size[i]][size[i]] (bilinear align_corners adjoint,
+ *                         gather form: deterministic, no atomics)
+ *   list_prep_volume_bwd  g [B][R][R][R][C] -> [B][C][R][R][R] */
+LIST_API int list_prep_maps_bwd(const float* g, const int32_t* ch, const int32_t* size, int32_t n_maps, int32_t B,
+                       int32_t map_size, float* const* grads_nchw, void* stream);
+LIST_API int list_prep_volume_bwd(const float* g, int32_t B, int32_t C, int32_t R, float* grad_ncdhw, void* stream);
+
 /* a-8 grid (reference utils.py:84-95): points [begin, begin+count) of the res^3 grid,
  * x slowest / z fastest, float64 linspace rounded to fp32, written as (x,y,z) rows. */
 LIST_API int list_grid_points(float* q, int32_t res, double bb_min, double bb_max, int64_t begin,

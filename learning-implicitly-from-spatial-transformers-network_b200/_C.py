@@ -66,6 +66,8 @@ SIGNATURES = {
     "list_feature_layout": (C.c_int, [_i32, _i32, _P(_i32), _P(ListLayout), _P(_i32)]),
     "list_prep_maps": (C.c_int, [_P(_vp), _P(_i32), _P(_i32), _i32, _i32, _i32, _vp, _i32, _vp]),
     "list_prep_volume": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _i32, _vp]),
+    "list_prep_maps_bwd": (C.c_int, [_vp, _P(_i32), _P(_i32), _i32, _i32, _i32, _P(_vp), _vp]),
+    "list_prep_volume_bwd": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "list_grid_points": (C.c_int, [_vp, _i32, _f64, _f64, _i64, _i64, _vp]),
     "list_gather_fwd": (C.c_int, [_P(ListCtx), _vp, _i32, _vp, _i64, _i32, _i64, _vp]),
     "list_gather_grid_fwd": (C.c_int, [_P(ListCtx), _i32, _i32, _f64, _f64, _i64, _i64, _vp, _i64, _vp]),

@@ -28,6 +28,8 @@ int cuda_fail(cudaError_t e, const char* what) {
 int prep_maps(const float* const* maps, const int32_t* ch, const int32_t* size, int n_maps, int B, int S, void* out,
               int dtype, cudaStream_t st);
 int prep_volume(const float* in, int B, int C, int R, void* out, int dtype, cudaStream_t st);
+int prep_volume_bwd(const float* g, int B, int C, int R, float* out, cudaStream_t st);
+int prep_maps_bwd(const float* g, const int32_t* ch, const int32_t* size, int n_maps, int B, int S, float* const* outs, cudaStream_t st);
 int gather_fwd(const ListCtx* ctx, const float* q, int q_is_raw, void* X, int64_t ldx, int B, int64_t N, cudaStream_t st);
 int gather_grid_fwd(const ListCtx* ctx, int image, int res, double bb_min, double bb_max, int64_t begin, int64_t count,
                     void* X, int64_t ldx, cudaStream_t st);
@@ -301,6 +303,23 @@ int list_prep_volume(const float* vol, int32_t B, int32_t C, int32_t R, void* ou
   LIST_CHECK_ARG(dtype == LIST_F32 || dtype == LIST_BF16, "list_prep_volume: bad dtype %d", dtype);
   LIST_CHECK_ARG(B >= 1 && C >= 1 && C <= 128 && R >= 1, "list_prep_volume: B=%d C=%d R=%d", B, C, R);
   return prep_volume(vol, B, C, R, out, dtype, static_cast<cudaStream_t>(stream));
+}
+
+int list_prep_maps_bwd(const float* g, const int32_t* ch, const int32_t* size, int32_t n_maps, int32_t B, int32_t map_size,
+                       float* const* grads_nchw, void* stream) {
+  LIST_CHECK_ARG(g && ch && size && grads_nchw, "list_prep_maps_bwd: NULL argument");
+  LIST_CHECK_ARG(n_maps >= 1 && n_maps <= LIST_MAX_MAPS, "list_prep_maps_bwd: n_maps %d out of range", n_maps);
+  LIST_CHECK_ARG(B >= 1 && map_size >= 2 && map_size <= 256, "list_prep_maps_bwd: B=%d map_size=%d (2..256)", B, map_size);
+  for (int i = 0; i < n_maps; ++i)
+    LIST_CHECK_ARG(grads_nchw[i] && ch[i] >= 1 && size[i] >= 1 && size[i] <= 1024 && static_cast<int64_t>(B) * ((ch[i] + 31) / 32) < 65536,
+                   "list_prep_maps_bwd: map %d invalid (C=%d, size=%d)", i, ch[i], size[i]);
+  return prep_maps_bwd(g, ch, size, n_maps, B, map_size, grads_nchw, static_cast<cudaStream_t>(stream));
+}
+
+int list_prep_volume_bwd(const float* g, int32_t B, int32_t C, int32_t R, float* grad_ncdhw, void* stream) {
+  LIST_CHECK_ARG(g && grad_ncdhw, "list_prep_volume_bwd: NULL argument");
+  LIST_CHECK_ARG(B >= 1 && B < 65536 && C >= 1 && C <= 128 && R >= 1, "list_prep_volume_bwd: B=%d C=%d R=%d", B, C, R);
+  return prep_volume_bwd(g, B, C, R, grad_ncdhw, static_cast<cudaStream_t>(stream));
 }
 
 int list_grid_points(float* q, int32_t res, double bb_min, double bb_max, int64_t begin, int64_t count, void* stream) {

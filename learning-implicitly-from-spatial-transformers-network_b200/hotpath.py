@@ -587,8 +587,9 @@ class _SdfFunction(torch.autograd.Function):
 
 
 class _PrepVolumeFn(torch.autograd.Function):
-    """NCDHW fp32 volume -> channels-last (B,R,R,R,C) through list_prep_volume; the backward is the inverse
-    permutation as a VIEW (no copy), so autograd continues into the voxel encoder."""
+    """NCDHW fp32 volume -> channels-last (B,R,R,R,C) through list_prep_volume; the backward is the inverse layout change
+    through list_prep_volume_bwd (a contiguous NCDHW gradient: what the voxel encoder's backward, or a leaf's .grad,
+    wants -- a permuted view would be copied element by element by whoever consumes it)."""
 
     @staticmethod
     def forward(ctx, vol):
@@ -602,12 +603,18 @@ class _PrepVolumeFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g.permute(0, 4, 1, 2, 3)
+        g = g.contiguous()
+        B, R, Cc = g.shape[0], g.shape[1], g.shape[4]
+        out = torch.empty(B, Cc, R, R, R, device=g.device, dtype=torch.float32)
+        with torch.cuda.device(g.device):
+            _C.check(_C.lib().list_prep_volume_bwd(g.data_ptr(), B, Cc, R, out.data_ptr(), _stream()), "list_prep_volume_bwd")
+        return out
 
 
 class _PrepMapsFn(torch.autograd.Function):
     """The five NCHW maps -> ONE upsampled channels-last (B,S,S,1024) tensor through list_prep_maps (row a-1, reference
-    modules.py:25-35); the backward splits the gradient per map and runs ATen's bilinear-upsample adjoint on it."""
+    modules.py:25-35); the backward is list_prep_maps_bwd (adjoint of the upsample + layout in one pass over the
+    channels-last gradient)."""
 
     @staticmethod
     def forward(ctx, map_size, *maps):
@@ -626,12 +633,12 @@ class _PrepMapsFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        S = ctx.map_size
-        grads, c0 = [], 0
-        for shp in ctx.shapes:
-            gi = g[..., c0:c0 + shp[1]].permute(0, 3, 1, 2).contiguous(memory_format=torch.channels_last)
-            grads.append(torch.ops.aten.upsample_bilinear2d_backward(gi, [S, S], list(shp), True, None, None))
-            c0 += shp[1]
+        g = g.contiguous()
+        grads = [torch.empty(shp, device=g.device, dtype=torch.float32) for shp in ctx.shapes]
+        with torch.cuda.device(g.device):
+            _C.check(_C.lib().list_prep_maps_bwd(g.data_ptr(), _C.i32_array([s[1] for s in ctx.shapes]),
+                                                 _C.i32_array([s[2] for s in ctx.shapes]), len(grads), g.shape[0], ctx.map_size,
+                                                 _C.ptr_array([t.data_ptr() for t in grads]), _stream()), "list_prep_maps_bwd")
         return (None, *grads)
 
 

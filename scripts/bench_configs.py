@@ -30,7 +30,7 @@ def timed(fn, warm=3, steps=5):
     return e0.elapsed_time(e1) / steps
 
 
-def cfg2():
+def cfg2(return_step=False):
     B, N, scale = 8, 2048, 10.0
     inp = synth.make_inputs(seed=synth.SEED, B=B, N=N, size="full", trans="camera", points="training")
     _, sdf_gt = synth.training_points(B, N, torch.Generator().manual_seed(synth.SEED + 1000))
@@ -57,6 +57,8 @@ def cfg2():
             ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, "fp32")
             kw = hotpath.prepare_weights(g.weights, ctx.layout, "fp32")
             return hotpath.query_sdf(ctx, kw, g.points)
+    if return_step:
+        return step
     ms = timed(step)
     ms_fwd = timed(hot_only)
     loss = float(step().item())

@@ -548,3 +548,31 @@ def test_parity_gate_cfg5_eight_images_per_gpu():
     ctx1, _ = ctx_and_weights(one, "bf16")
     alone = hotpath.grid_sdf(ctx1, kw, res, begin=res ** 3 // 2, count=65536, sdf_scale=10.0, chunk_rows=65536).cpu()
     assert torch.equal(alone[0], full[3, res ** 3 // 2: res ** 3 // 2 + 65536])
+
+
+def test_prep_adjoints_match_torch_autograd():
+    """list_prep_maps_bwd / list_prep_volume_bwd (row a-9: autograd of reference modules.py:25-35 and of the layout change)
+    against torch's own backward of F.interpolate(align_corners=True) + permute, on full-size tensors."""
+    import torch.nn.functional as F
+    inp = synth.make_inputs(seed=91, B=2, N=8, size="full", trans="camera")
+    g = inp.to("cuda:0")
+    maps = [m.clone().requires_grad_(True) for m in g.maps]
+    vols = [v.clone().requires_grad_(True) for v in g.vols]
+    maps_cl = hotpath.prep_maps_autograd(maps)
+    vols_cl = [hotpath.prep_volume_autograd(v) for v in vols]
+    gen = torch.Generator(device="cuda:0").manual_seed(5)
+    up = torch.randn(maps_cl.shape, device="cuda:0", generator=gen)
+    ups = [torch.randn(v.shape, device="cuda:0", generator=gen) for v in vols_cl]
+    torch.autograd.backward([maps_cl, *vols_cl], [up, *ups])
+    ours = [m.grad.clone() for m in maps] + [v.grad.clone() for v in vols]
+    maps2 = [m.detach().clone().requires_grad_(True) for m in g.maps]
+    vols2 = [v.detach().clone().requires_grad_(True) for v in g.vols]
+    ref_cl = torch.cat([F.interpolate(m, size=(137, 137), mode="bilinear", align_corners=True) for m in maps2], dim=1).permute(0, 2, 3, 1)
+    assert torch.allclose(ref_cl, maps_cl, atol=1e-5, rtol=1e-5)
+    refv = [v.permute(0, 2, 3, 4, 1) for v in vols2]
+    torch.autograd.backward([ref_cl, *refv], [up, *ups])
+    theirs = [m.grad for m in maps2] + [v.grad for v in vols2]
+    for i, (a, b) in enumerate(zip(ours, theirs)):
+        assert a.shape == b.shape and a.is_contiguous()
+        err = (a - b).abs().max().item()
+        assert err <= 1e-4 * max(1.0, b.abs().max().item()), (i, err)
