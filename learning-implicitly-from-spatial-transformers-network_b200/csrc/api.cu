@@ -198,11 +198,15 @@ static int hook_download(const GridHooks* h, const float* sdf_dev, int64_t off, 
 
 // Runs `n_items` (gather_i -> mlp_i) pairs.  gather(i, X, stream) fills X; mlp(i, X, stream) consumes it.
 // xbuf[0], xbuf[1]: two feature-row buffers; with overlap == false only xbuf[0] is used, serially on `st`.
-template <typename G, typename M>
-static int run_chunks(int64_t n_items, void* const xbuf[2], bool overlap, cudaStream_t st, G gather, M mlp) {
+// pre (optional part of gather(i) that may run early): with `pre_ahead` the pre-stage of item 1 is enqueued right after
+// item 0's, before gather(0) -- its buffer is free at the start, and whatever gather(0) has to wait for (tensors that are
+// still being uploaded) then has two items' worth of independent work in front of it.
+template <typename P, typename G, typename M>
+static int run_chunks(int64_t n_items, void* const xbuf[2], bool overlap, cudaStream_t st, bool pre_ahead, P pre, G gather, M mlp) {
   int rc;
   if (!overlap || n_items < 2) {
     for (int64_t i = 0; i < n_items; ++i) {
+      if ((rc = pre(i, xbuf[0], st))) return rc;
       if ((rc = gather(i, xbuf[0], st))) return rc;
       if ((rc = mlp(i, xbuf[0], st))) return rc;
     }
@@ -216,6 +220,8 @@ static int run_chunks(int64_t n_items, void* const xbuf[2], bool overlap, cudaSt
   for (int64_t i = 0; i < n_items; ++i) {
     const int b = static_cast<int>(i & 1);
     if (i >= 2) LIST_CUDA(cudaStreamWaitEvent(p->lo, p->freed[b], 0));   // MLP of item i-2 has read xbuf[b]
+    if (!(i == 1 && pre_ahead) && (rc = pre(i, xbuf[b], p->lo))) return rc;
+    if (i == 0 && pre_ahead && (rc = pre(1, xbuf[1], p->lo))) return rc;
     if ((rc = gather(i, xbuf[b], p->lo))) return rc;
     LIST_CUDA(cudaEventRecord(p->ready[b], p->lo));
     LIST_CUDA(cudaStreamWaitEvent(p->hi, p->ready[b], 0));
@@ -667,7 +673,8 @@ int list_sdf_fwd(const ListCtx* ctx, const ListWeights* w, const float* q, int32
     n = (N - n0 < chunk_rows) ? (N - n0) : chunk_rows;
   };
   return run_chunks(
-      per_image * B, xbuf, two && overlap_enabled(), st,
+      per_image * B, xbuf, two && overlap_enabled(), st, false,
+      [](int64_t, void*, cudaStream_t) { return LIST_OK; },
       [&](int64_t i, void* X, cudaStream_t s) {
         int b; int64_t n0, n;
         span(i, b, n0, n);
@@ -728,16 +735,22 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
     if (xr_bytes + g_bytes + grid_plan_bytes(res, res - 1, chunk_rows) <= xb) {
       void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
       if ((rc = hoist::prepare(ctx, w, pl3, hbuf, st))) return rc;
+      // the line tables and the plans only read the projected tensors; everything uploaded late is first read by the rest
+      // kernel -- with a late upload pending, two chunks' tables and plans are enqueued in front of it
+      const bool late_pending = !late_done && hooks && hooks->late;
       return run_chunks(
-          per_image * ctx->B, xbuf, overlap_enabled(), st,
+          per_image * ctx->B, xbuf, overlap_enabled(), st, late_pending,
           [&](int64_t i, void* X, cudaStream_t s) -> int {
             int b; int64_t n0, n;
             span(i, b, n0, n);
             char* const G = static_cast<char*>(X) + xr_bytes;
-            int r2 = hoist::lines(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, G, s);
-            if (r2) return r2;
-            if ((r2 = grid_plan(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, G, G + g_bytes, s))) return r2;
-            // the line tables only read the projected tensors; everything uploaded late is first read by the rest kernel
+            const int r2 = hoist::lines(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, G, s);
+            return r2 ? r2 : grid_plan(ctx, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, G, G + g_bytes, s);
+          },
+          [&](int64_t i, void* X, cudaStream_t s) -> int {
+            int b; int64_t n0, n;
+            span(i, b, n0, n);
+            int r2;
             if (i == 0 && !late_done && hooks && hooks->late && (r2 = hook_late(hooks, s))) return r2;
             return hoist::gather(ctx, w, pl3, hbuf, b, res, bb_min, bb_max, begin + n0, n, static_cast<__nv_bfloat16*>(X) - 512, k_f,
                                  hoist::kPartRest | hoist::kPartOnes, s);
@@ -759,7 +772,8 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
     void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
     if ((rc = hoist::prepare(ctx, w, pl, hbuf, st))) return rc;
     return run_chunks(
-        per_image * ctx->B, xbuf, overlap_enabled(), st,
+        per_image * ctx->B, xbuf, overlap_enabled(), st, false,
+        [](int64_t, void*, cudaStream_t) { return LIST_OK; },
         [&](int64_t i, void* X, cudaStream_t s) -> int {
           int b; int64_t n0, n;
           span(i, b, n0, n);
@@ -782,7 +796,8 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
   }
   if (!late_done && (rc = hook_late(hooks, st))) return rc;
   return run_chunks(
-      per_image * ctx->B, xbuf, two && overlap_enabled(), st,
+      per_image * ctx->B, xbuf, two && overlap_enabled(), st, false,
+      [](int64_t, void*, cudaStream_t) { return LIST_OK; },
       [&](int64_t i, void* X, cudaStream_t s) {
         int b; int64_t n0, n;
         span(i, b, n0, n);
