@@ -285,7 +285,7 @@ def main():
         g = inp.to(dev)
         ctx = hotpath.prepare_context(g.maps, g.vols, g.trans_mat, a.dtype)
         kw = hotpath.prepare_weights(g.weights, ctx.layout, a.dtype)
-        ws = hotpath._workspace(ctx.struct(), kw.struct(), chunk, dev)
+        ws = hotpath._workspace(ctx.struct(), kw.struct(), chunk, dev, res)
         # the kernels write the rank's shard straight into its piece of the all_gather input (no staging copies)
         shard_buf, local_out = parallel.shard_buffer(total, rank, world, 1, dev, align=res * res)
         local_out = local_out if local_out.is_contiguous() else local_out.contiguous()

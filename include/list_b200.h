@@ -252,7 +252,12 @@ LIST_API int list_grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const vo
                      float* dbg_h1, int64_t* trace, uint64_t* stats, void* stream);
 
 /* a-8 (reference executors.py:191-231): SDF of grid points [begin, begin+count) of every
- * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e. */
+ * image, sdf[B][count], divided by sdf_scale.  This is the per-rank shard of §8e.
+ * Workspace: list_sdf_grid_workspace_bytes(ctx, w, res, chunk_rows) bytes -- what the path that runs for this
+ * configuration and resolution needs (bf16 line-table path: two chunk buffers of ~1.6 KB per row + 0.3 GB of projected
+ * tensors per image, e.g. 13 GB for 4 M-row chunks of a 256^3 grid); list_sdf_workspace_bytes(ctx, w, chunk_rows) is a
+ * resolution-independent upper bound (full feature rows) and is accepted as well. */
+LIST_API size_t list_sdf_grid_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int32_t res, int64_t chunk_rows);
 LIST_API int list_sdf_grid(const ListCtx* ctx, const ListWeights* w, int32_t res, double bb_min,
                   double bb_max, int64_t begin, int64_t count, float* sdf, float sdf_scale,
                   int64_t chunk_rows, void* workspace, size_t workspace_bytes, void* stream);

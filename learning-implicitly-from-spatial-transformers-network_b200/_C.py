@@ -93,6 +93,7 @@ SIGNATURES = {
     "list_grid_tc_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _f64, _f64, _i64, _i64, _vp, _i64, _vp, _vp, _f32, _vp,
                                    _vp, _vp, _vp]),
     "list_sdf_workspace_bytes": (_sz, [_P(ListCtx), _P(ListWeights), _i64]),
+    "list_sdf_grid_workspace_bytes": (_sz, [_P(ListCtx), _P(ListWeights), _i32, _i64]),
     "list_sdf_fwd": (C.c_int, [_P(ListCtx), _P(ListWeights), _vp, _i32, _i32, _i64, _vp, _f32, _i64, _vp, _sz, _vp]),
     "list_sdf_grid": (C.c_int, [_P(ListCtx), _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _vp, _f32, _i64, _vp, _sz, _vp]),
     "list_sdf_grid_late": (C.c_int, [_P(ListCtx), _P(ListWeights), _i32, _f64, _f64, _i64, _i64, _vp, _f32, _i64, _vp, _sz, _vp,

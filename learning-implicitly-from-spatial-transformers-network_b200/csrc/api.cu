@@ -432,6 +432,57 @@ size_t list_sdf_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int64_
   return (ctx->dtype == LIST_BF16 ? 2 * xb : xb) + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256) + extra;
 }
 
+// Workspace layout of the dense-grid call for a given resolution: which path runs (env switches are read here, at the
+// time of the call) and where its pieces live.  [chunk buffer 0 | chunk buffer 1 (bf16) | MLP workspace | hoisted tensors]
+namespace {
+struct GridWs {
+  int path;                          // 0: full feature rows (fp32, or no hoisted path), 1: addend-kernel path, 2: line-table path
+  size_t xb, mlp_off, hoist_off, total;
+  size_t xr_bytes, g_bytes;          // line-table path: pieces of a chunk buffer [Xr | G | plans]
+  hoist::Plan pl;
+};
+int grid_ws_plan(const ListCtx* ctx, const ListWeights* w, int res, int64_t chunk_rows, GridWs* g) {
+  ListLayout lay;
+  const int rc = list_feature_layout(ctx->map_channels, ctx->n_levels, ctx->vol_ch, &lay, nullptr);
+  if (rc) return rc;
+  const bool two = ctx->dtype == LIST_BF16;
+  const size_t mlp_ws = align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+  g->path = 0;
+  g->xr_bytes = g->g_bytes = 0;
+  g->xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
+  size_t hoisted = 0;
+  if (two && hoist_enabled()) {
+    if (lines_enabled() && hoist::make_plan(ctx, w, &g->pl, kLinesLevels, kLinesMaxRes) == LIST_OK &&
+        hoist::check_gather(ctx, g->pl, res) == LIST_OK) {
+      const int k_f = g->pl.k_h - 512;
+      g->xr_bytes = align_up(static_cast<size_t>(chunk_rows) * k_f * 2, 256);
+      g->g_bytes = align_up(hoist::lines_bytes(g->pl, res, res - 1, chunk_rows), 256);   // worst case: the chunk starts on a line's last point
+      const size_t need = align_up(g->xr_bytes + g->g_bytes + grid_plan_bytes(res, res - 1, chunk_rows), 256);
+      if (need <= g->xb) {             // (tiny grids: a line's tables outweigh its few rows -- the addend path takes those)
+        g->xb = need;
+        g->path = 2;
+        hoisted = align_up(g->pl.total, 256);
+      }
+    }
+    if (g->path == 0 && hoist::make_plan(ctx, w, &g->pl) == LIST_OK && hoist::check_gather(ctx, g->pl, res) == LIST_OK) {
+      g->xb = align_up(static_cast<size_t>(chunk_rows) * g->pl.k_h * 2, 256);
+      g->path = 1;
+      hoisted = align_up(g->pl.total, 256);
+    }
+  }
+  g->mlp_off = two ? 2 * g->xb : g->xb;
+  g->hoist_off = g->mlp_off + mlp_ws;
+  g->total = g->hoist_off + hoisted;
+  return LIST_OK;
+}
+}  // namespace
+
+size_t list_sdf_grid_workspace_bytes(const ListCtx* ctx, const ListWeights* w, int32_t res, int64_t chunk_rows) {
+  if (!ctx || !w || chunk_rows <= 0 || res < 1 || check_ctx(ctx) || check_weights(w, -1)) return 0;
+  GridWs g;
+  return grid_ws_plan(ctx, w, res, chunk_rows, &g) == LIST_OK ? g.total : 0;
+}
+
 size_t list_hoist_bytes(const ListCtx* ctx, const ListWeights* w) {
   if (!ctx || !w) return 0;
   hoist::Plan pl;
@@ -706,16 +757,18 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
   LIST_CHECK_ARG(sdf != nullptr && sdf_scale != 0.f && chunk_rows >= 1, "list_sdf_grid: sdf NULL, sdf_scale 0 or chunk_rows < 1");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   bool late_done = false;
-  const size_t need = list_sdf_workspace_bytes(ctx, w, chunk_rows);
-  if (workspace == nullptr || workspace_bytes < need) {
-    set_error("list_sdf_grid: workspace %zu B < required %zu B", workspace_bytes, need);
+  GridWs gw;
+  if ((rc = grid_ws_plan(ctx, w, res, chunk_rows, &gw))) return rc;
+  if (workspace == nullptr || workspace_bytes < gw.total) {
+    set_error("list_sdf_grid: workspace %zu B < required %zu B (list_sdf_grid_workspace_bytes)", workspace_bytes, gw.total);
     return LIST_ENOMEM;
   }
-  const size_t xb = align_up(static_cast<size_t>(chunk_rows) * lay.k_pad * elem_size(ctx->dtype), 256);
+  const size_t xb = gw.xb;
   const bool two = ctx->dtype == LIST_BF16;
   void* const xbuf[2] = {workspace, two ? static_cast<char*>(workspace) + xb : workspace};
-  const size_t mlp_off = two ? 2 * xb : xb;
+  const size_t mlp_off = gw.mlp_off;
   void* mlp_ws = static_cast<char*>(workspace) + mlp_off;
+  void* const hbuf = static_cast<char*>(workspace) + gw.hoist_off;
   const int64_t per_image = (count + chunk_rows - 1) / chunk_rows;
   auto span = [&](int64_t i, int& b, int64_t& n0, int64_t& n) {
     b = static_cast<int>(i / per_image);
@@ -726,14 +779,11 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
   // call (hoist::prepare); per chunk, lines.cu reduces the projected levels to one column table per z-line, the rest
   // kernel writes the non-hoisted feature columns, and grid_tc.cu interpolates the hoisted terms on the tensor cores inside
   // the MLP kernel.  A chunk's buffer holds [Xr: rows x k_f | G: line tables].
-  hoist::Plan pl3;
-  if (two && hoist_enabled() && lines_enabled() && hoist::make_plan(ctx, w, &pl3, kLinesLevels, kLinesMaxRes) == LIST_OK &&
-      hoist::check_gather(ctx, pl3, res) == LIST_OK) {
+  if (gw.path == 2) {
+    const hoist::Plan& pl3 = gw.pl;
     const int k_f = pl3.k_h - 512;
-    const size_t xr_bytes = align_up(static_cast<size_t>(chunk_rows) * k_f * 2, 256);
-    const size_t g_bytes = align_up(hoist::lines_bytes(pl3, res, res - 1, chunk_rows), 256);      // worst case: the chunk starts on a line's last point
-    if (xr_bytes + g_bytes + grid_plan_bytes(res, res - 1, chunk_rows) <= xb) {
-      void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+    const size_t xr_bytes = gw.xr_bytes, g_bytes = gw.g_bytes;
+    {
       if ((rc = hoist::prepare(ctx, w, pl3, hbuf, st))) return rc;
       // the line tables and the plans only read the projected tensors; everything uploaded late is first read by the rest
       // kernel -- with a late upload pending, two chunks' tables and plans are enqueued in front of it
@@ -767,9 +817,8 @@ static int grid_impl(const ListCtx* ctx, const ListWeights* w, int32_t res, doub
   // bf16, addend-kernel path (round 1; LIST_B200_LINES=0 or a configuration the line-table path does not cover): the
   // per-chunk gather writes the hoisted row [addend 512 | 832 columns]; fc_0 runs on the 832 columns and adds the addend
   // block in its epilogue.
-  hoist::Plan pl;
-  if (two && hoist_enabled() && hoist::make_plan(ctx, w, &pl) == LIST_OK && hoist::check_gather(ctx, pl, res) == LIST_OK) {
-    void* hbuf = static_cast<char*>(workspace) + mlp_off + align_up(list_mlp_workspace_bytes(w, chunk_rows), 256);
+  if (gw.path == 1) {
+    const hoist::Plan& pl = gw.pl;
     if ((rc = hoist::prepare(ctx, w, pl, hbuf, st))) return rc;
     return run_chunks(
         per_image * ctx->B, xbuf, overlap_enabled(), st, false,

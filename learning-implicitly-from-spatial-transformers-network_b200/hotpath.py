@@ -383,11 +383,27 @@ def mlp(weights: KernelWeights, X: torch.Tensor, out_div: float = 1.0, return_wo
     return (sdf, ws) if return_workspace else sdf
 
 
-def _workspace(ctx_s, w_s, chunk_rows, dev):
-    need = _C.lib().list_sdf_workspace_bytes(C.byref(ctx_s), C.byref(w_s), chunk_rows)
+def _workspace(ctx_s, w_s, chunk_rows, dev, res: Optional[int] = None):
+    """Workspace of list_sdf_fwd (res None: full feature rows) or of the dense-grid calls at resolution `res` (what the
+    path that runs needs; much smaller for the bf16 line-table path)."""
+    if res is None:
+        need = _C.lib().list_sdf_workspace_bytes(C.byref(ctx_s), C.byref(w_s), chunk_rows)
+    else:
+        need = _C.lib().list_sdf_grid_workspace_bytes(C.byref(ctx_s), C.byref(w_s), res, chunk_rows)
     if need == 0:
-        raise RuntimeError("list_sdf_workspace_bytes returned 0 (invalid ctx/weights)")
+        raise RuntimeError("workspace size query returned 0 (invalid ctx/weights)")
     return torch.empty(need, device=dev, dtype=torch.uint8)
+
+
+def fit_grid_chunk(ctx: HotPathContext, weights: KernelWeights, res: int, chunk_rows: int, fraction: float = 0.6,
+                   floor: int = 65536) -> int:
+    """Largest chunk_rows <= the requested one whose dense-grid workspace fits into `fraction` of the device memory that is
+    free right now (halving; never below `floor`)."""
+    cs, wsn = ctx.struct(), weights.struct()
+    free = torch.cuda.mem_get_info(ctx.maps_cl.device)[0]
+    while chunk_rows > floor and _C.lib().list_sdf_grid_workspace_bytes(C.byref(cs), C.byref(wsn), res, chunk_rows) > fraction * free:
+        chunk_rows //= 2
+    return max(chunk_rows, 1)
 
 
 def query_sdf(ctx: HotPathContext, weights: KernelWeights, points: torch.Tensor, raw: bool = True,
@@ -423,7 +439,7 @@ def grid_sdf(ctx: HotPathContext, weights: KernelWeights, res: int, begin: int =
         return out
     chunk_rows = max(1, min(chunk_rows, count))
     cs, wsn = ctx.struct(), weights.struct()
-    ws = workspace if workspace is not None else _workspace(cs, wsn, chunk_rows, dev)
+    ws = workspace if workspace is not None else _workspace(cs, wsn, chunk_rows, dev, res)
     with torch.cuda.device(dev):
         _C.check(_C.lib().list_sdf_grid(C.byref(cs), C.byref(wsn), res, bb_min, bb_max, begin, count, out.data_ptr(),
                                         float(sdf_scale), chunk_rows, ws.data_ptr(), ws.numel(), _stream()),

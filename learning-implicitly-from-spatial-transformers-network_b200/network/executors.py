@@ -79,11 +79,14 @@ class LIST:
         ctx = net.encode(img, transmat, unsqueeze_dim=0 if img.shape[0] == 1 else 1)
         res = self.grid_res
         total = res ** 3
-        grid = parallel.sharded_grid(
-            # results do not depend on the chunking (tests), so the kernels get large launches instead of the
-            # reference's 65 536-point chunks: the last partial wave of gather CTAs is amortised
-            lambda begin, count: net.grid(ctx, res, begin, count, self.sdf_scale, max(self.test_pointnum, min(4194304, max(524288, -(-count // 4))))),
-            total, align=res * res)
+        def shard(begin, count):
+            # results do not depend on the chunking (tests), so the kernels get large launches instead of the reference's
+            # 65 536-point chunks (the last partial wave of CTAs is amortised, four chunks keep the pipeline busy) -- as
+            # large as the memory that is free right now allows (test_pointnum stays the lower bound)
+            want = max(self.test_pointnum, min(4194304, max(524288, -(-count // 4))))
+            chunk = hotpath.fit_grid_chunk(ctx, net._weights(ctx), res, want, floor=max(1, min(self.test_pointnum, want)))
+            return net.grid(ctx, res, begin, count, self.sdf_scale, chunk)
+        grid = parallel.sharded_grid(shard, total, align=res * res)
         self._grid_dev = grid[0].view(res, res, res)                  # kept on the device for the mesh extraction
         vals = self._grid_dev.cpu().numpy()
         return vals, ctx

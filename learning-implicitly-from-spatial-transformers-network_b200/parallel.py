@@ -171,7 +171,7 @@ class ShardedHostRunner:
         staged = len(self.stages) > 1
         ctx = hp.prepare_context(maps, vols, T, self.dtype, skip_levels=self.late_levels if staged else ())
         if self.workspace is None:
-            self.workspace = hp._workspace(ctx.struct(), self.weights.struct(), self.chunk, self.dev)
+            self.workspace = hp._workspace(ctx.struct(), self.weights.struct(), self.chunk, self.dev, self.res)
         late = [vols[l] if (staged and l in self.late_levels) else None for l in range(len(vols))]
         hp.grid_sdf_late(ctx, self.weights, self.res, self.begin, self.count, sdf_scale, self.chunk, self.out_dev,
                          self.workspace, self.stages[-1]["event"] if staged else None, late, out_host=self.out_host)

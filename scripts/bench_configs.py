@@ -78,7 +78,7 @@ def grid_cfg(name, B, res, mode):
     chunk = 1048576 if mode == "bf16" else 131072
     out = torch.empty(B, total, device=DEV, dtype=torch.float32)
     cs, wsn = ctx.struct(), kw.struct()
-    ws = hotpath._workspace(cs, wsn, chunk, DEV)
+    ws = hotpath._workspace(cs, wsn, chunk, DEV, res)
     ms = timed(lambda: hotpath.grid_sdf(ctx, kw, res, 0, total, 10.0, chunk, out=out, workspace=ws))
     return {"config": name, "dtype": mode, "images": B, "grid_res": res, "ms_per_step": ms,
             "queries_per_sec": B * total / (ms * 1e-3), "checksum": float(out.double().sum().item())}
