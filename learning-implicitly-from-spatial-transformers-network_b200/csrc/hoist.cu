@@ -69,9 +69,14 @@ struct RestParams {
   int R[kRestLevels], C[kRestLevels], xoff[kRestLevels];   // xoff: first column of the level in the hoisted row
   int cells_max[kRestLevels];       // table rows per (level, displacement)
   int toff[kRestLevels];            // first float of the level's tables in shared memory
-  int dstr[kRestLevels];            // floats between the tables of consecutive displacements: cells_max * C plus 4 floats of
-                                    // padding for the vector levels, so that the 16-byte accesses of the lanes of a warp (one
-                                    // per (displacement, channel vector)) spread over the banks instead of hitting the same ones
+  // Tables of a level in shared memory: displacements 0, 1, 2 do not move (H, D), so they share ONE table (`cells_u` cells:
+  // the union of the three W-shift classes' ranges); 3..6 have one each (cells_max cells).  dbase[d]: first float of
+  // displacement d's table relative to toff.  Each table is followed by 4 floats of padding for the vector levels, so that
+  // the 16-byte accesses of the lanes of a warp (one per (displacement, channel vector)) spread over the banks.
+  int dbase[kRestLevels][LIST_NUM_DISP];
+  int cells_u[kRestLevels];
+  int g_lanes5[kRestLevels];        // phase G: kRestThreads / (5 tables * ncv)
+  float inv_combos5[kRestLevels];
   int tab_floats;                   // floats of all column tables (the per-step tables follow)
   int nvl, nsl;                     // vector levels [0, nvl), scalar levels [nvl, nvl + nsl)
   int lwarp0[kRestLevels + 1];      // phase L: warps [lwarp0[i], lwarp0[i+1]) work on vector level i
@@ -344,9 +349,10 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   __shared__ float s_q0[kTile];
   // per (level, class, step), sized by the tile length and placed behind the column tables in dynamic shared memory:
   // voxel index relative to the class's first one (fits a byte: cells_max <= 255) and the weight of its right neighbour
-  float* const s_w1 = s_tab + p.tab_floats;                                         // [nlev*3][kPz]
-  unsigned char* const s_rel = reinterpret_cast<unsigned char*>(s_w1 + kRestLevels * 3 * p.tm.kPz);   // [nlev*3][kPz]
+  uint2* const s_sw = reinterpret_cast<uint2*>(s_tab + p.tab_floats);               // [nlev*3][kPz]: {bits of w1, rel}
   __shared__ int s_first[kRestLevels][3], s_ncell[kRestLevels][3];
+  __shared__ int s_coff[kRestLevels][3];                // first cell of the class relative to the shared table of d = 0, 1, 2
+  __shared__ int s_firstu[kRestLevels], s_ncellu[kRestLevels];
   __shared__ Corner s_cor[kRestLevels * LIST_NUM_DISP][4];
   __shared__ int s_tailtab[kMaxTail];                   // scalar columns: table base | (level*3+class) << 24
   const int tid = threadIdx.x;
@@ -358,11 +364,20 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
   // ---- phase 0: per-step voxel index / weight per (level, class); corners; descriptors ----
   if (tid < nlev * 3) {
     const int li = tid / 3, cls = tid % 3;
-    const float sh = class_shift(cls);
-    const int a = axis_border(step_q0(p.tm, t, t.s_lo) + sh, p.R[li]).i0;
-    const int b = axis_border(step_q0(p.tm, t, t.s_hi - 1) + sh, p.R[li]).i0;
+    int a = 0, n = 0, lo = 1 << 30, hi = 0;                           // this class's range and the union of the three
+    for (int k = 0; k < 3; ++k) {
+      const float sh = class_shift(k);
+      const int ak = axis_border(step_q0(p.tm, t, t.s_lo) + sh, p.R[li]).i0;
+      const int bk = axis_border(step_q0(p.tm, t, t.s_hi - 1) + sh, p.R[li]).i0;
+      const int nk = min(min(bk + 1, p.R[li] - 1) - ak + 1, p.cells_max[li]);
+      if (k == cls) { a = ak; n = nk; }
+      lo = min(lo, ak);
+      hi = max(hi, ak + nk);
+    }
     s_first[li][cls] = a;
-    s_ncell[li][cls] = min(min(b + 1, p.R[li] - 1) - a + 1, p.cells_max[li]);
+    s_ncell[li][cls] = n;
+    s_coff[li][cls] = a - lo;
+    if (cls == 0) { s_firstu[li] = lo; s_ncellu[li] = min(hi - lo, p.cells_u[li]); }
   } else if (tid >= 32 && tid < 32 + nlev * LIST_NUM_DISP) {
     const int pr = tid - 32, li = pr / LIST_NUM_DISP, d = pr % LIST_NUM_DISP;
     uint32_t base[4];
@@ -380,7 +395,7 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       const int rel = col - p.xoff[li];
       if (rel >= 0 && rel < LIST_NUM_DISP * p.C[li]) {
         const int d = rel / p.C[li], c = rel % p.C[li];
-        val = (p.toff[li] + d * p.dstr[li] + c) | ((li * 3 + shift_class(d)) << 24);
+        val = (p.toff[li] + p.dbase[li][d] + c) | (d < 3 ? 1 << 23 : 0) | ((li * 3 + shift_class(d)) << 24);   // bit 23: shared table
       }
     }
     s_tailtab[j] = val;
@@ -396,26 +411,26 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       rel = min(ax.i0 - s_first[li][cls], p.cells_max[li] - 1);
       w1 = ax.w1;
     }
-    s_rel[lc * kPz + s] = static_cast<unsigned char>(rel);
-    s_w1[lc * kPz + s] = w1;
+    s_sw[lc * kPz + s] = make_uint2(__float_as_uint(w1), static_cast<uint32_t>(rel));
   }
 
   // ---- phase G: vector levels.  A thread keeps one (displacement, channel vector) -- corners, weights and base pointers
   //      stay in registers -- and strides over the voxel cells of its class ----
   {
     for (int li = 0; li < p.nvl; ++li) {
-      const int C = p.C[li], ncv = C >> 3, cm = p.cells_max[li];
-      const int combos = LIST_NUM_DISP * ncv;                           // <= kMaxVec <= kRestThreads / 2
-      const int lanes = p.g_lanes[li];                                  // kRestThreads / combos
-      const int lane0 = fast_div(tid, p.inv_combos[li]), combo = tid - lane0 * combos;
+      const int C = p.C[li], ncv = C >> 3;
+      const int combos = 5 * ncv;                                       // tables 0 (shared by d = 0, 1, 2), 3, 4, 5, 6
+      const int lanes = p.g_lanes5[li];                                 // kRestThreads / combos
+      const int lane0 = fast_div(tid, p.inv_combos5[li]), combo = tid - lane0 * combos;
       if (lane0 >= lanes) continue;
-      const int d = combo >> p.lg_ncv[li], cvv = combo - (d << p.lg_ncv[li]);
-      const int cls = shift_class(d);
+      const int tt = combo >> p.lg_ncv[li], cvv = combo - (tt << p.lg_ncv[li]);
+      const int d = tt == 0 ? 0 : tt + 2;
       const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
       const Corner c0 = cor[0], c1 = cor[1], c2 = cor[2], c3 = cor[3];
-      const int ncell = s_ncell[li][cls];
-      const __nv_bfloat16* __restrict__ src = p.vols[li] + static_cast<uint32_t>(s_first[li][cls] + lane0) * C + cvv * 8;
-      float* __restrict__ dstt = s_tab + p.toff[li] + d * p.dstr[li] + lane0 * C + cvv * 8;
+      const int ncell = tt == 0 ? s_ncellu[li] : s_ncell[li][0];
+      const int first = tt == 0 ? s_firstu[li] : s_first[li][0];
+      const __nv_bfloat16* __restrict__ src = p.vols[li] + static_cast<uint32_t>(first + lane0) * C + cvv * 8;
+      float* __restrict__ dstt = s_tab + p.toff[li] + p.dbase[li][d] + lane0 * C + cvv * 8;
       const int sstep = lanes * C;
       // the four corner loads of the next cell are issued before this cell's arithmetic (two register sets)
       auto issue = [&](const __nv_bfloat16* sp, uint4 (&r)[4]) {
@@ -453,23 +468,23 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
     }
     // scalar levels (C % 8 != 0): one (displacement, cell, channel) value per item
     for (int li = p.nvl; li < nlev; ++li) {
-      const int C = p.C[li], cm = p.cells_max[li];
-      const int per_d = cm * C, cnt = LIST_NUM_DISP * per_d;
-      const float inv_per_d = 1.0f / static_cast<float>(per_d), inv_c = 1.0f / static_cast<float>(C);
+      const int C = p.C[li];
+      const int per_t = p.cells_u[li] * C, cnt = 5 * per_t;               // five tables, enumerated with the shared one's size
+      const float inv_per_t = 1.0f / static_cast<float>(per_t), inv_c = 1.0f / static_cast<float>(C);
       const __nv_bfloat16* __restrict__ vol = p.vols[li];
       for (int it = tid; it < cnt; it += kRestThreads) {
-        const int d = fast_div(it, inv_per_d);
-        const int rem = it - d * per_d;
+        const int tt = fast_div(it, inv_per_t);
+        const int rem = it - tt * per_t;
         const int c = fast_div(rem, inv_c);
         const int ch = rem - c * C;
-        const int cls = shift_class(d);
-        if (c >= s_ncell[li][cls]) continue;
+        const int d = tt == 0 ? 0 : tt + 2;
+        if (c >= (tt == 0 ? s_ncellu[li] : s_ncell[li][0])) continue;
         const Corner* cor = s_cor[li * LIST_NUM_DISP + d];
-        const __nv_bfloat16* src = vol + static_cast<uint32_t>(s_first[li][cls] + c) * C + ch;
+        const __nv_bfloat16* src = vol + static_cast<uint32_t>((tt == 0 ? s_firstu[li] : s_first[li][0]) + c) * C + ch;
         float r = __bfloat162float(src[cor[0].base]) * cor[0].w;
 #pragma unroll
         for (int k = 1; k < 4; ++k) r = fmaf(__bfloat162float(src[cor[k].base]), cor[k].w, r);
-        s_tab[p.toff[li] + d * p.dstr[li] + c * C + ch] = r;
+        s_tab[p.toff[li] + p.dbase[li][d] + c * C + ch] = r;
       }
     }
   }
@@ -494,30 +509,41 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
       const int d = v >> p.lg_ncv[li], cvv = v - (d << p.lg_ncv[li]);
       const int cls = shift_class(d);
       const int sr0 = blk * per, sr1 = min(nsteps, sr0 + per);
-      const unsigned char* __restrict__ rels = s_rel + (li * 3 + cls) * kPz + t.s_lo;
-      const float* __restrict__ w1s = s_w1 + (li * 3 + cls) * kPz + t.s_lo;
+      const uint2* __restrict__ sw = s_sw + (li * 3 + cls) * kPz + t.s_lo;
       const int last = s_ncell[li][cls] - 1;
-      const float* __restrict__ tab = s_tab + p.toff[li] + d * p.dstr[li] + cvv * 8;
-      float G0[8], Dv[8];
-      int cc = -1;
+      const float* __restrict__ tab = s_tab + p.toff[li] + p.dbase[li][d] + (d < 3 ? s_coff[li][cls] * C : 0) + cvv * 8;
+      // G0 / G1: the columns of the current voxel cell and of its right neighbour, Dv = G1 - G0 (packed pairs).  When the
+      // walk moves on by one cell the old right neighbour becomes the new left one: only one column is read again.
+      float2 G0[4], G1[4], Dv[4];
+      int cc = -2;
       __nv_bfloat16* __restrict__ dst = Xb + static_cast<int64_t>(sr0) * p.ldx + p.xoff[li] + d * C + cvv * 8;
+      const float2 minus1 = make_float2(-1.f, -1.f);
       for (int sr = sr0; sr < sr1; ++sr, dst += p.ldx) {
-        const int c = rels[sr];
+        const uint2 e = sw[sr];
+        const int c = static_cast<int>(e.y);
         if (c != cc) {
-          cc = c;
-          const float* g0p = tab + c * C;
-          const float* g1p = tab + min(c + 1, last) * C;
-          const float4 a0 = *reinterpret_cast<const float4*>(g0p), a1 = *reinterpret_cast<const float4*>(g0p + 4);
-          const float4 b0 = *reinterpret_cast<const float4*>(g1p), b1 = *reinterpret_cast<const float4*>(g1p + 4);
-          G0[0] = a0.x; G0[1] = a0.y; G0[2] = a0.z; G0[3] = a0.w; G0[4] = a1.x; G0[5] = a1.y; G0[6] = a1.z; G0[7] = a1.w;
-          Dv[0] = b0.x - a0.x; Dv[1] = b0.y - a0.y; Dv[2] = b0.z - a0.z; Dv[3] = b0.w - a0.w;
-          Dv[4] = b1.x - a1.x; Dv[5] = b1.y - a1.y; Dv[6] = b1.z - a1.z; Dv[7] = b1.w - a1.w;
-        }
-        const float w1 = w1s[sr];
-        float out[8];
+          if (c == cc + 1) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) out[j] = fmaf(Dv[j], w1, G0[j]);
-        store8(dst, out);
+            for (int j = 0; j < 4; ++j) G0[j] = G1[j];
+          } else {
+            const float4 a0 = *reinterpret_cast<const float4*>(tab + c * C), a1 = *reinterpret_cast<const float4*>(tab + c * C + 4);
+            G0[0] = make_float2(a0.x, a0.y); G0[1] = make_float2(a0.z, a0.w); G0[2] = make_float2(a1.x, a1.y); G0[3] = make_float2(a1.z, a1.w);
+          }
+          const float* g1p = tab + min(c + 1, last) * C;
+          const float4 b0 = *reinterpret_cast<const float4*>(g1p), b1 = *reinterpret_cast<const float4*>(g1p + 4);
+          G1[0] = make_float2(b0.x, b0.y); G1[1] = make_float2(b0.z, b0.w); G1[2] = make_float2(b1.x, b1.y); G1[3] = make_float2(b1.z, b1.w);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) Dv[j] = ffma2(G0[j], minus1, G1[j]);          // G1 - G0, one rounding
+          cc = c;
+        }
+        const float w1 = __uint_as_float(e.x);
+        const float2 ww = make_float2(w1, w1);
+        uint4 o;
+        { const float2 r = ffma2(Dv[0], ww, G0[0]); o.x = pack_bf16x2(r.x, r.y); }
+        { const float2 r = ffma2(Dv[1], ww, G0[1]); o.y = pack_bf16x2(r.x, r.y); }
+        { const float2 r = ffma2(Dv[2], ww, G0[2]); o.z = pack_bf16x2(r.x, r.y); }
+        { const float2 r = ffma2(Dv[3], ww, G0[3]); o.w = pack_bf16x2(r.x, r.y); }
+        *reinterpret_cast<uint4*>(dst) = o;
       }
     }
   }
@@ -548,12 +574,14 @@ __global__ void __launch_bounds__(kRestThreads) hoist_rest_kernel(const RestPara
         float val = 0.f;
         if (col < nscal) {
           const int tt = s_tailtab[col];
-          const int lc = tt >> 24, tab = tt & 0xffffff;
+          const int lc = tt >> 24;
           const int li = lc / 3, cls = lc - li * 3;
-          const int c = s_rel[lc * kPz + s];
+          const int tab = (tt & 0x7fffff) + ((tt >> 23) & 1) * s_coff[li][cls] * p.C[li];
+          const uint2 e = s_sw[lc * kPz + s];
+          const int c = static_cast<int>(e.y);
           const int c1 = min(c + 1, s_ncell[li][cls] - 1);
           const float g0 = s_tab[tab + c * p.C[li]], g1 = s_tab[tab + c1 * p.C[li]];
-          val = fmaf(g1 - g0, s_w1[lc * kPz + s], g0);
+          val = fmaf(g1 - g0, __uint_as_float(e.x), g0);
         } else if (col < nscal + 3) {
           const int a = col - nscal;
           val = a == 0 ? s_q0[s] : (a == 1 ? t.qy : t.qz);
@@ -707,6 +735,8 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       r.lg_ncv[i] = lg;
       r.g_lanes[i] = kRestThreads / combos;
       r.inv_combos[i] = 1.0f / static_cast<float>(combos);
+      r.g_lanes5[i] = kRestThreads / (5 * ncv);
+      r.inv_combos5[i] = 1.0f / static_cast<float>(5 * ncv);
       const int nblk = (w[i] * 32) / combos > 1 ? (w[i] * 32) / combos : 1;
       r.l_nblk[i] = nblk;
       r.inv_lnblk[i] = 1.0f / static_cast<float>(nblk);
@@ -728,10 +758,20 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       int cm = span + 3;
       if (cm > r.R[i]) cm = r.R[i];
       r.cells_max[i] = cm;
+      // shared table of d = 0, 1, 2: the classes' first cells differ by at most the W shift in cells (+1 for rounding)
+      int cu = cm + 2 * (static_cast<int>(kDisplacement * 0.5f * static_cast<float>(r.R[i] - 1)) + 2);
+      if (cu > r.R[i]) cu = r.R[i];
+      r.cells_u[i] = cu;
       r.toff[i] = static_cast<int>(floats);
-      r.dstr[i] = cm * r.C[i] + (i < r.nvl ? 4 : 0);
-      floats += static_cast<size_t>(LIST_NUM_DISP) * r.dstr[i];
-      if (i < r.nvl) items += LIST_NUM_DISP * cm * (r.C[i] / 8);
+      const int pad = i < r.nvl ? 4 : 0;
+      int off = 0;
+      for (int d = 0; d < LIST_NUM_DISP; ++d) {
+        r.dbase[i][d] = d < 3 ? 0 : off;
+        if (d == 2) off = cu * r.C[i] + pad;
+        else if (d > 2) off += cm * r.C[i] + pad;
+      }
+      floats += static_cast<size_t>(off);
+      if (i < r.nvl) items += 5 * cu * (r.C[i] / 8);
     }
     static const size_t budget = []() {                // LIST_B200_REST_SMEM_KB: table budget per CTA (tuning aid)
       const char* e = getenv("LIST_B200_REST_SMEM_KB");
@@ -744,7 +784,7 @@ static int build_rest(const ListCtx* ctx, const Plan& pl, const ListLayout& lay,
       r.g_items = items;
       r.tm.kPz = kpz;
       r.tab_floats = static_cast<int>((floats + 3) / 4 * 4);
-      *smem = static_cast<size_t>(r.tab_floats) * 4 + static_cast<size_t>(kRestLevels) * 3 * kpz * (4 + 1);
+      *smem = static_cast<size_t>(r.tab_floats) * 4 + static_cast<size_t>(kRestLevels) * 3 * kpz * 8;   // + the per-step {w1, rel} tables
       return LIST_OK;
     }
   }
