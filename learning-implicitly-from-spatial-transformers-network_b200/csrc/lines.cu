@@ -39,10 +39,11 @@ struct LinesParams {
   TileMap tm;
 };
 
-struct DispGeo {                        // per (level, displacement) of a CTA
-  uint32_t z0, z1;                      // element offsets of the two D planes
-  float wz0, wz1;
-  int yn[kNY];                          // H node indices (clamped to the volume)
+struct __align__(16) DispGeo {          // per (level, displacement) of a CTA
+  uint32_t off0[kNY];                   // element offsets of the kNY rows (node 0, channel 0) in the first D plane, displacement slab included
+  float wz0;
+  uint32_t off1[kNY];                   // ... in the second D plane
+  float wz1;
 };
 
 // 4 consecutive bf16 channels (8-byte access)
@@ -81,8 +82,8 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
     displaced(q, d, pd);
     const Axis3 az = axis_border(pd[2], R);
     DispGeo g;
-    g.z0 = static_cast<uint32_t>(az.i0) * R * R * kN0L;
-    g.z1 = static_cast<uint32_t>(az.i1) * R * R * kN0L;
+    const uint32_t z0 = static_cast<uint32_t>(az.i0) * R * R * kN0L + static_cast<uint32_t>(d) * p.dstride[h];
+    const uint32_t z1 = static_cast<uint32_t>(az.i1) * R * R * kN0L + static_cast<uint32_t>(d) * p.dstride[h];
     g.wz0 = az.w0; g.wz1 = az.w1;
     int ybase = 0;
     bool two = true;
@@ -102,7 +103,11 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
     }
     for (int j = 0; j < LY; ++j) s_wy[h][d][j][3] = two ? 1.f : 0.f;
 #pragma unroll
-    for (int k = 0; k < kNY; ++k) g.yn[k] = min(ybase + k, R - 1);
+    for (int k = 0; k < kNY; ++k) {
+      const uint32_t yo = static_cast<uint32_t>(min(ybase + k, R - 1)) * R * kN0L;
+      g.off0[k] = z0 + yo;
+      g.off1[k] = z1 + yo;
+    }
     s_geo[h][d] = g;
   }
   __syncthreads();
@@ -124,20 +129,19 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
   for (int h = 0; h < p.nh; ++h) {
     const int R = p.R[h];
     const __nv_bfloat16* __restrict__ pv = p.pvol[h] + v * 4;
-    const uint32_t ds = p.dstride[h];
     if (ig >= R) continue;
     float2 acc[LY][2];
     auto issue = [&](int i, int sq, uint2 (&r0)[kNY], uint2 (&r1)[kNY]) {
       const int d = sq == 0 ? 0 : (sq < 5 ? sq + 2 : sq - 4);
-      const DispGeo& g = s_geo[h][d];
-      const __nv_bfloat16* __restrict__ pd = pv + static_cast<size_t>(d) * ds + static_cast<uint32_t>(i) * kN0L;
+      const uint4 o0 = *reinterpret_cast<const uint4*>(s_geo[h][d].off0), o1 = *reinterpret_cast<const uint4*>(s_geo[h][d].off1);
+      const uint32_t f0[kNY] = {o0.x, o0.y, o0.z}, f1[kNY] = {o1.x, o1.y, o1.z};
+      const __nv_bfloat16* __restrict__ pd = pv + static_cast<uint32_t>(i) * kN0L;
       const bool two = s_wy[h][d][0][3] != 0.f;                   // uniform over the CTA
 #pragma unroll
       for (int k = 0; k < kNY; ++k) {
         if (k < 2 || !two) {
-          const uint32_t yo = static_cast<uint32_t>(g.yn[k]) * R * kN0L;
-          r0[k] = __ldg(reinterpret_cast<const uint2*>(pd + g.z0 + yo));
-          r1[k] = __ldg(reinterpret_cast<const uint2*>(pd + g.z1 + yo));
+          r0[k] = __ldg(reinterpret_cast<const uint2*>(pd + f0[k]));
+          r1[k] = __ldg(reinterpret_cast<const uint2*>(pd + f1[k]));
         }
       }
     };
