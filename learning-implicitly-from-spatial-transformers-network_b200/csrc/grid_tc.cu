@@ -162,7 +162,7 @@ __device__ __forceinline__ uint32_t bf16_bits(float x) { return static_cast<uint
 // ------------------------------------------------------------------ tile plans
 // One CTA of 128 threads per tile, thread = step.  Writes hdr[tile] (64-row chunks), rows[tile][..] (source address of
 // every listed row, padded with the zero row to a whole chunk) and ent[tile][step][..] (weight entries).
-__global__ void __launch_bounds__(BM) grid_plan_kernel(const Geo p, const PlanBuf out) {
+__global__ void __launch_bounds__(BM, 12) grid_plan_kernel(const Geo p, const PlanBuf out) {
   __shared__ int s_key[BM], s_ckey[BM], s_cbase[BM], s_cmask[BM];
   __shared__ short s_cslot[BM * 4];
   __shared__ int s_first[NC], s_last[NC], s_scan[8];
