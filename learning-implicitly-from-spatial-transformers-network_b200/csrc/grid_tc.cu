@@ -13,7 +13,8 @@
 //                      +  Aw[128 x rows] . Brows[rows x 512]           (I chunks: Aw = interpolation weights written by the
 //                                                                       interp warps, Brows = rows of P / G copied with
 //                                                                       cp.async; MN-major B operand)
-// followed by bias + ReLU, fc_1, fc_2, fc_out exactly as mlp_tc.cu (activations stay in TMEM).  The 512-wide "addend"
+// (fc_0's bias included: Xr carries 1.0 in three pad columns, the weight copy of hoist::prepare the bf16 hi / mid / lo
+// parts of b0) followed by ReLU, fc_1, fc_2, fc_out as in mlp_tc.cu (activations stay in TMEM).  The 512-wide "addend"
 // block of round 1 (34 GB through HBM per 256^3 grid) no longer exists.
 //
 //   Warp roles : warp 0 = TMA producer and ring allocator, warp 1 = TMEM allocator + MMA issuer (one thread),
@@ -90,8 +91,8 @@ inline PlanBuf plan_carve(void* buf, unsigned n_tiles) {
 }
 
 // ---- shared-memory carve-up of grid_tc_kernel (offsets from the 1024-byte aligned base) ----
-constexpr int OFF_PAR = NU * UNIT_BYTES;                           // b0 b1 b2 w3 (fp32)
-constexpr int PARAM_FLOATS = N0 + N1 + N2 + N2;
+constexpr int OFF_PAR = NU * UNIT_BYTES;                           // b1 b2 w3 (fp32; b0 rides in the MMA)
+constexpr int PARAM_FLOATS = N1 + N2 + N2;
 constexpr int OFF_ENT = OFF_PAR + PARAM_FLOATS * 4;                // this CTA's tile: uint32 [128][kEntPad]
 constexpr int OFF_ROWS = OFF_ENT + kPlanEntBytes;                  // uint64 [2][kMaxRows]: both tiles' row lists
 constexpr int OFF_PART = OFF_ROWS + 2 * kPlanRowBytes;               // float [128]: fc_out partial sums of the upper column halves
@@ -113,7 +114,7 @@ struct Geo {
 };
 
 struct Params {
-  const float *b0, *b1, *b2, *w3, *b3;
+  const float *b1, *b2, *w3, *b3;
   float* sdf;                       // [count] of this image
   float out_div;
   int nkF;                          // F chunks: (k_pad - hoist_cols) / 64
@@ -356,8 +357,7 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* const gbase = smem_raw + (base - raw);
   float* const s_par = reinterpret_cast<float*>(gbase + OFF_PAR);
-  float* const s_b0 = s_par;
-  float* const s_b1 = s_b0 + N0;
+  float* const s_b1 = s_par;
   float* const s_b2 = s_b1 + N1;
   float* const s_w3 = s_b2 + N2;
   const uint32_t bar0 = base + OFF_BAR;
@@ -420,10 +420,9 @@ grid_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   if (warp >= kEpiWarp0 && warp < kIntWarp0) {
     for (int i = threadIdx.x - kEpiWarp0 * 32; i < PARAM_FLOATS; i += kEpiWarps * 32) {
       float v;
-      if (i < N0) v = __ldg(p.b0 + i);
-      else if (i < N0 + N1) v = __ldg(p.b1 + i - N0);
-      else if (i < N0 + N1 + N2) v = __ldg(p.b2 + i - N0 - N1);
-      else v = __ldg(p.w3 + i - N0 - N1 - N2);
+      if (i < N1) v = __ldg(p.b1 + i);
+      else if (i < N1 + N2) v = __ldg(p.b2 + i - N1);
+      else v = __ldg(p.w3 + i - N1 - N2);
       s_par[i] = v;
     }
   }
@@ -954,7 +953,7 @@ int grid_tc_fwd(const ListCtx* ctx, const ListWeights* w, const hoist::Plan& pl,
   LIST_CHECK_ARG((reinterpret_cast<uintptr_t>(Xr) & 15) == 0 && (reinterpret_cast<uintptr_t>(plan_buf) & 255) == 0,
                  "grid_tc: Xr must be 16-byte and the plan buffer 256-byte aligned");
   Params p{};
-  p.b0 = w->b0; p.b1 = w->b1; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;
+  p.b1 = w->b1; p.b2 = w->b2; p.w3 = w->w3; p.b3 = w->b3;       // b0: in the weight copy of hoist::prepare (Plan::bias_col)
   p.sdf = sdf;
   p.out_div = out_div;
   p.nkF = k_f / BK;

@@ -285,11 +285,7 @@ __global__ void __launch_bounds__(ltc::kThreads, 1) hoist_lines_tc_kernel(const 
                              "r"(u[i].x), "r"(u[i].y), "r"(u[i].z), "r"(u[i].w) : "memory");
               }
             } else {
-#ifdef LT_NO_STORE
-              if (live && v[0] == 0x7fc01234u) {
-#else
               if (live) {
-#endif
 #pragma unroll
                 for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(dst + c * 32 + 8 * i) = u[i];
               }
@@ -315,11 +311,7 @@ __global__ void __launch_bounds__(ltc::kThreads, 1) hoist_lines_tc_kernel(const 
               __syncwarp();
               for (int sub = 0; sub * p.ly < 32; ++sub) {
                 const int bc = (quarter * 32 + sub * p.ly) / p.ly;
-#ifdef LT_NO_STORE
-                const uint32_t on = 0;
-#else
                 const uint32_t on = (lane == 0 && bc < 3) ? 1u : 0u;
-#endif
                 tma_store_4d(&tmG, buf + static_cast<uint32_t>(sub * p.ly) * 128u, half * BN + (c >> 1) * 64,
                              p.rowbase[h] + bc * p.R[h] + node, ly0, static_cast<int>(plane), on);
               }
@@ -357,12 +349,8 @@ __global__ void __launch_bounds__(ltc::kThreads, 1) hoist_lines_tc_kernel(const 
             const int k = k0 + u * kProdWarps;
             if (k < kpad) {
               r[u] = s_krow[h * BK + k];
-#ifndef LT_NO_LOAD
               a0[u] = __ldg(reinterpret_cast<const uint4*>(src + r[u].off0));
               a1[u] = __ldg(reinterpret_cast<const uint4*>(src + r[u].off1));
-#else
-              a0[u] = make_uint4(k, k, k, k); a1[u] = a0[u];
-#endif
             }
           }
 #pragma unroll
