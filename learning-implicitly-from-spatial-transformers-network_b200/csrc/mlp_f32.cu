@@ -12,11 +12,10 @@ static bool f32_tc() {
   const char* e = getenv("LIST_B200_F32_TC");
   return !(e && e[0] == '0');
 }
-// floats of the lo(x) copies the tensor-core GEMMs read next to the forward's activations: X, H1, H2 and the three
-// weight matrices
-static size_t fwd_lo_floats(const ListWeights* w, int64_t rows) {
-  return static_cast<size_t>(rows) * (w->k_pad + w->n0 + w->n1) + static_cast<size_t>(w->n0) * w->k_pad +
-         static_cast<size_t>(w->n1) * w->n0 + static_cast<size_t>(w->n2) * w->n1;
+// floats of the lo(w) copies of the three weight matrices the tensor-core GEMMs read next to the forward's activations
+// (lo of the activations themselves is computed inside tgemm_kernel)
+static size_t fwd_lo_floats(const ListWeights* w, int64_t) {
+  return static_cast<size_t>(w->n0) * w->k_pad + static_cast<size_t>(w->n1) * w->n0 + static_cast<size_t>(w->n2) * w->n1;
 }
 
 // sdf[r] = (sum_k H3[r][k]*w3[k] + b3) / out_div   -- one warp per row.
@@ -35,7 +34,7 @@ __global__ void __launch_bounds__(256) fc_out_kernel(const float* __restrict__ H
 }
 
 size_t mlp_f32_workspace_bytes(const ListWeights* w, int64_t rows) {
-  // H1 H2 H3 | lo(X) lo(H1) lo(H2) lo(W0) lo(W1) lo(W2)
+  // H1 H2 H3 | lo(W0) lo(W1) lo(W2)
   return (static_cast<size_t>(rows) * (w->n0 + w->n1 + w->n2) + fwd_lo_floats(w, rows)) * sizeof(float);
 }
 
@@ -58,23 +57,18 @@ int mlp_f32_fwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows,
   const float* W1 = static_cast<const float*>(w->w1);
   const float* W2 = static_cast<const float*>(w->w2);
   if (!exact && f32_tc() && ldx == w->k_pad) {
-    float* Xl = H3 + rows * w->n2;
-    float* H1l = Xl + rows * w->k_pad;
-    float* H2l = H1l + rows * w->n0;
-    float* W0l = H2l + rows * w->n1;
+    float* W0l = H3 + rows * w->n2;
     float* W1l = W0l + static_cast<size_t>(w->n0) * w->k_pad;
     float* W2l = W1l + static_cast<size_t>(w->n1) * w->n0;
-    if ((rc = split_lo(X, Xl, rows * w->k_pad, st))) return rc;
+    // lo of the activations (X, H1, H2) is computed inside tgemm_kernel from the operand box in shared memory
     if ((rc = split_lo(W0, W0l, static_cast<int64_t>(w->n0) * w->k_pad, st))) return rc;
     if ((rc = split_lo(W1, W1l, static_cast<int64_t>(w->n1) * w->n0, st))) return rc;
     if ((rc = split_lo(W2, W2l, static_cast<int64_t>(w->n2) * w->n1, st))) return rc;
-    if ((rc = tgemm(X, Xl, ldx, W0, W0l, w->k_pad, H1, w->n0, M, w->n0, w->k_pad, ep, st))) return rc;
-    if ((rc = split_lo(H1, H1l, rows * w->n0, st))) return rc;
+    if ((rc = tgemm(X, nullptr, ldx, W0, W0l, w->k_pad, H1, w->n0, M, w->n0, w->k_pad, ep, st))) return rc;
     ep.bias = w->b1;
-    if ((rc = tgemm(H1, H1l, w->n0, W1, W1l, w->n0, H2, w->n1, M, w->n1, w->n0, ep, st))) return rc;
-    if ((rc = split_lo(H2, H2l, rows * w->n1, st))) return rc;
+    if ((rc = tgemm(H1, nullptr, w->n0, W1, W1l, w->n0, H2, w->n1, M, w->n1, w->n0, ep, st))) return rc;
     ep.bias = w->b2;
-    if ((rc = tgemm(H2, H2l, w->n1, W2, W2l, w->n1, H3, w->n2, M, w->n2, w->n1, ep, st))) return rc;
+    if ((rc = tgemm(H2, nullptr, w->n1, W2, W2l, w->n1, H3, w->n2, M, w->n2, w->n1, ep, st))) return rc;
   } else {
     rc = sgemm<true, true>(X, ldx, W0, w->k_pad, H1, w->n0, M, w->n0, w->k_pad, ep, st);
     if (rc) return rc;
@@ -186,14 +180,13 @@ int mlp_f32_bwd(const ListWeights* w, const float* X, int64_t ldx, int64_t rows,
                      float* dPrev, const GemmEpilogue& epPrev) -> int {
       int r;
       if ((r = colsum(dZ, n, db))) return r;
-      if ((r = split_lo(dZ, dZl, rows * n, st))) return r;
       if (dW) {
         if ((r = transpose_split(dZ, n, M, n, dZT, dZTl, ldr, st))) return r;
         if ((r = transpose_split(Xin, ldin, M, k, XT, XTl, ldr, st))) return r;
         if ((r = tgemm(dZT, dZTl, ldr, XT, XTl, ldr, dW, k, n, k, M, acc, st))) return r;
       }
       if ((r = transpose_split(W, k, n, k, WT, WTl, n, st))) return r;
-      return tgemm(dZ, dZl, n, WT, WTl, n, dPrev, k, M, k, n, epPrev, st);
+      return tgemm(dZ, nullptr, n, WT, WTl, n, dPrev, k, M, k, n, epPrev, st);   // lo(dZ) in the kernel
     };
     mask.mask = H2; mask.ldmask = w->n1;
     if ((rc = layer(dZ2, w->n2, H2, w->n1, w->n1, W2, g->d_w2, g->d_b2, dZ1, mask))) return rc;

@@ -29,7 +29,7 @@ constexpr int ST = 2;
 constexpr int A_BYTES = BM * BKF * 4, B_BYTES = BN * BKF * 4;
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;          // A, lo(A), B, lo(B)
 constexpr int BAR_OFF = ST * STAGE_BYTES;
-constexpr int SMEM_BYTES = BAR_OFF + (2 * ST + 1) * 8 + 16 + 1024;
+constexpr int SMEM_BYTES = BAR_OFF + (3 * ST + 1) * 8 + 16 + 1024;       // full, empty, ready (lo(A) in place) | dfull
 constexpr int kThreads = 192;
 
 // Instruction descriptor: D = f32, A = B = tf32, both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
@@ -41,10 +41,23 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
 }
+// hi(x) = the upper 19 bits of x -- exactly what the tensor core makes of the 32-bit operand it is handed (measured on
+// B200: it truncates; with lo = x - round_to_tf32(x) the corrected product is no better than plain TF32).  lo(x) = x - hi(x)
+// is exact in fp32 with up to 13 significant bits, of which the tensor core again keeps the upper 11: lo is therefore
+// rounded to nearest TF32 HERE, so that what is lost (<= 2^-23 |x|) is unbiased instead of a truncation that always
+// points towards zero and adds up over K.
+__device__ __forceinline__ float tf32_lo(float x) {
+  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
+  return __uint_as_float(r);
+}
+// inline_lo_a: lo(A) is not streamed from memory but computed from the A box in shared memory by the four epilogue warps
+// (idle during the main loop otherwise), so the activations need neither a lo tensor nor the pass that writes it.
 __global__ void __launch_bounds__(kThreads, 1)
 tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
              const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl,
-             float* __restrict__ C, int64_t ldc, int M, int N, int K, GemmEpilogue ep) {
+             float* __restrict__ C, int64_t ldc, int M, int N, int K, GemmEpilogue ep, int inline_lo_a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -52,9 +65,10 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const uint32_t bar0 = base + BAR_OFF;
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (ST + s); };
-  const uint32_t dfull_bar = bar0 + 8u * (2 * ST);
+  auto ready_bar = [&](int s) { return bar0 + 8u * (2 * ST + s); };
+  const uint32_t dfull_bar = bar0 + 8u * (3 * ST);
   const uint32_t tmem_slot = dfull_bar + 8u;
-  volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + BAR_OFF + (2 * ST + 1) * 8);
+  volatile uint32_t* const tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gbase + BAR_OFF + (3 * ST + 1) * 8);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   // K range of this z-slice (whole chunks of BKF)
@@ -65,7 +79,7 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmAl); tma_prefetch_desc(&tmB); tma_prefetch_desc(&tmBl);
-    for (int s = 0; s < ST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < ST; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 4); }
     mbar_init(dfull_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -83,13 +97,13 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (i >= ST) mbar_wait(empty_bar(s), ((i / ST) - 1) & 1);
           const uint32_t st = base + s * STAGE_BYTES;
           const int k0 = (kc0 + i) * BKF;
-          mbar_expect_tx(full_bar(s), STAGE_BYTES);
+          mbar_expect_tx(full_bar(s), inline_lo_a ? STAGE_BYTES - A_BYTES : STAGE_BYTES);
           const CUtensorMap* am[2] = {&tmA, &tmAl};
           const CUtensorMap* bm[2] = {&tmB, &tmBl};
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const uint32_t a = st + h * A_BYTES, b = st + 2 * A_BYTES + h * B_BYTES;
-            tma_load_2d<1>(am[h], full_bar(s), a, k0, m0);                       // box {32 k, 128 m}
+            if (h == 0 || !inline_lo_a) tma_load_2d<1>(am[h], full_bar(s), a, k0, m0);   // box {32 k, 128 m}
             tma_load_2d<1>(bm[h], full_bar(s), b, k0, n0);                       // box {32 k, 256 n}
           }
         }
@@ -99,7 +113,8 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         constexpr uint32_t idesc = idesc_tf32();
         for (int i = 0; i < nk; ++i) {
           const int s = i % ST;
-          mbar_wait(full_bar(s), (i / ST) & 1);
+          if (inline_lo_a) mbar_wait(ready_bar(s), (i / ST) & 1);     // the epilogue warps wrote lo(A) (they waited for `full`)
+          else mbar_wait(full_bar(s), (i / ST) & 1);
           tc_fence_after();
           const uint32_t st = base + s * STAGE_BYTES;
           const uint32_t a[2] = {st, st + A_BYTES}, b[2] = {st + 2 * A_BYTES, st + 2 * A_BYTES + B_BYTES};
@@ -124,6 +139,25 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int quarter = warp & 3;
       const uint32_t tq = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const int m = m0 + quarter * 32 + lane;
+      if (inline_lo_a) {
+        // lo(A) box = elementwise transform of the A box (same 128B-swizzled layout, so the same offsets): 1024 16-byte
+        // pieces per stage, 8 per thread
+        const int t = (warp - 2) * 32 + lane;
+        for (int i = 0; i < nk; ++i) {
+          const int s = i % ST;
+          mbar_wait_warp(full_bar(s), (i / ST) & 1);
+          const float4* src = reinterpret_cast<const float4*>(gbase + s * STAGE_BYTES);
+          float4* dst = reinterpret_cast<float4*>(gbase + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+          for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+            const float4 v = src[t + j * 128];
+            dst[t + j * 128] = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_local(ready_bar(s));
+        }
+      }
       mbar_wait_warp(dfull_bar, 0);
       tc_fence_after();
       const bool atomic = gridDim.z > 1;
@@ -177,17 +211,6 @@ tgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
 }
 
-// hi(x) = the upper 19 bits of x -- exactly what the tensor core makes of the 32-bit operand it is handed (measured on
-// B200: it truncates; with lo = x - round_to_tf32(x) the corrected product is no better than plain TF32).  lo(x) = x - hi(x)
-// is exact in fp32 with up to 13 significant bits, of which the tensor core again keeps the upper 11: lo is therefore
-// rounded to nearest TF32 HERE, so that what is lost (<= 2^-23 |x|) is unbiased instead of a truncation that always
-// points towards zero and adds up over K.
-__device__ __forceinline__ float tf32_lo(float x) {
-  const float lo = x - __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(lo));
-  return __uint_as_float(r);
-}
 __global__ void __launch_bounds__(256) split_lo_kernel(const float* __restrict__ x, float* __restrict__ lo, int64_t n4) {
   for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
@@ -239,7 +262,7 @@ static int launch(const float* A, const float* Alo, int64_t lda, const float* B,
   CUtensorMap tmA, tmAl, tmB, tmBl;
   int rc;
   if ((rc = make_map_f32(&tmA, A, K, M, lda, BM))) return rc;
-  if ((rc = make_map_f32(&tmAl, Alo, K, M, lda, BM))) return rc;
+  if ((rc = make_map_f32(&tmAl, Alo ? Alo : A, K, M, lda, BM))) return rc;   // Alo == nullptr: lo(A) is computed in the kernel
   if ((rc = make_map_f32(&tmB, B, K, N, ldb, BN))) return rc;
   if ((rc = make_map_f32(&tmBl, Blo, K, N, ldb, BN))) return rc;
   dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN);
@@ -258,7 +281,7 @@ static int launch(const float* A, const float* Alo, int64_t lda, const float* B,
     LIST_CUDA(cudaFuncSetAttribute(tgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_dev = dev;
   }
-  tgemm_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmA, tmAl, tmB, tmBl, C, ldc, M, N, K, ep);
+  tgemm_kernel<<<grid, kThreads, SMEM_BYTES, st>>>(tmA, tmAl, tmB, tmBl, C, ldc, M, N, K, ep, Alo == nullptr ? 1 : 0);
   LIST_LAUNCH_CHECK("tgemm_kernel");
   return LIST_OK;
 }
