@@ -11,8 +11,9 @@
 //
 //   C[m][n] (+)= epi( sum_k A[m*lda + k] * B[n*ldb + k] )      both operands K-major, epilogue as sgemm.cuh
 // Both operands are K-major (MN-major TF32 operands returned zeros in bring-up; the backward transposes its operands
-// instead: transpose_split_kernel).  The lo parts are separate tensors written by split_lo_kernel / transpose_split_kernel
-// (one elementwise pass per operand); TMA streams 128-byte
+// instead: transpose_split_kernel).  The lo parts of the weights and of the transposed operands are separate tensors
+// written by split_lo_kernel / transpose_split_kernel; lo(A) of an activation operand (Alo == nullptr) is computed in the
+// kernel from the A box in shared memory by the epilogue warps.  TMA streams 128-byte
 // swizzled fp32 boxes of x and lo(x) for both operands into a 2-stage ring (96 KB per stage: 128 x 32 of A, 256 x 32 of
 // B, each twice), one thread issues three tcgen05.mma.kind::tf32 (M = 128, N = 256, K = 8) per k-step, four epilogue
 // warps drain the 128 x 256 fp32 accumulator from TMEM with bias / ReLU / ReLU-mask / accumulate (atomics under split-K).
