@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from list_b200 import synth
+from list_b200 import hotpath, synth
 from list_b200.network import executors, models, modules
 from oracle import mcubes_oracle as MC
 from oracle import ref_port as P
@@ -119,3 +119,39 @@ def test_list_forward_training_mode_reaches_every_trainable_stage():
         assert any(gr is not None and gr.abs().sum() > 0 for _, gr in named), name
         if missing:
             print(f"{name}: no gradient for {missing}")
+
+
+def test_kernel_weight_cache_under_threaded_replicas():
+    """nn.DataParallel replicas share the module's __dict__ shallowly, so every replica thread sees the same cache dict
+    (reference train.py:126, test.py:62 wrap the model that way).  Threads asking for different (device, dtype) slots --
+    here the two compute dtypes on one device -- must each get the object built for THEIR slot from THEIR parameters."""
+    import copy
+    import threading
+    from list_b200.network import modules as M
+    torch.manual_seed(0)
+    dec = M.VoxelDecoder2(3610, 256).cuda()
+    layout = hotpath.feature_layout(1024, [1, 16, 32, 64, 128, 128])
+    replicas = [copy.copy(dec) for _ in range(4)]                  # shallow: the cache dict is shared, like DataParallel's replicate
+    assert all(r._cache is dec._cache for r in replicas)
+    errors = []
+
+    def worker(rep, dtype, rounds=25):
+        try:
+            want = torch.bfloat16 if dtype == "bf16" else torch.float32
+            ref_w1 = rep.fc["fc_1"].weight.detach().squeeze(-1).to(want)
+            for _ in range(rounds):
+                kw = rep.kernel_weights(layout, dtype)
+                if kw.w0.dtype != want or not kw.w0.is_cuda:
+                    errors.append((dtype, str(kw.w0.dtype)))
+                elif not torch.equal(kw.w1.reshape(ref_w1.shape), ref_w1):
+                    errors.append((dtype, "w1 mismatch"))
+        except Exception as e:                                     # noqa: BLE001
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=worker, args=(replicas[i], "bf16" if i % 2 else "fp32")) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    torch.cuda.synchronize()
+    assert not errors, errors[:3]
