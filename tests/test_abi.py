@@ -75,3 +75,19 @@ def test_staged_and_host_entry_points_reject_bad_arguments_without_a_gpu():
                                 1.0, 8, None, None, 0, None)
     assert rc == _C.EINVAL and "NULL argument" in _C.last_error()
     assert lib.list_sdf_grid_host_bytes(None, None, 5, 137, 6, None, None, 1, _C.BF16, 8, 8) == 0
+
+
+def test_round2_entry_points_reject_bad_arguments_without_a_gpu():
+    """The entry points added in round 2 validate before any CUDA work, and the size queries are pure host arithmetic."""
+    lib = _C.lib()
+    assert lib.list_sdf_grid_workspace_bytes(None, None, 64, 1024) == 0
+    rc = lib.list_prep_maps_bwd(None, None, None, 5, 1, 137, None, None)
+    assert rc == _C.EINVAL and "NULL argument" in _C.last_error()
+    rc = lib.list_prep_volume_bwd(None, 1, 16, 8, None, None)
+    assert rc == _C.EINVAL and "NULL argument" in _C.last_error()
+    rc = lib.list_grid_tc_fwd(None, None, None, 8, -0.5, 0.5, 0, 8, None, 384, None, None, 1.0, None, None, None, None)
+    assert rc == _C.EINVAL
+    # plans: 19 KB per tile of 128 steps (+ header); a 256^3 chunk of 4 M rows has 32768 tiles
+    n = lib.list_grid_plan_bytes(256, 0, 4194304)
+    assert 32768 * (832 * 8 + 128 * 24 * 4) <= n <= 32768 * (832 * 8 + 128 * 24 * 4) + 32768 * 4 + 512
+    assert lib.list_grid_plan_bytes(256, 0, 0) == 0
