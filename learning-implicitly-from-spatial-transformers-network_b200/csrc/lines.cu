@@ -122,7 +122,9 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
   }
   if (jlo >= jhi) return;
   const int64_t out_line0 = lz * res + ly0 - p.line_first;       // may be negative for the lines below jlo
+  const int line_stride = p.rpl * kN0L;                           // elements between the tables of consecutive lines
   const int v = tid & 127, ig = tid >> 7;                        // 4-channel vector, node group
+  __nv_bfloat16* const gline = p.G + out_line0 * line_stride + v * 4;   // (before the buffer for the lines below jlo: never stored)
   // Steps of a thread: (node i, displacement in class order 0 3 4 5 6 | 1 | 2).  The six row loads of step n + 1 are issued
   // before step n's arithmetic (two register sets, the loop is unrolled by two), so the loads' latency -- the kernel's
   // dominant stall at 16 warps per SM -- hides behind ~100 FMAs; a class's rows are stored when its last step is done.
@@ -134,15 +136,15 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
     auto issue = [&](int i, int sq, uint2 (&r0)[kNY], uint2 (&r1)[kNY]) {
       const int d = sq == 0 ? 0 : (sq < 5 ? sq + 2 : sq - 4);
       const uint4 o0 = *reinterpret_cast<const uint4*>(s_geo[h][d].off0), o1 = *reinterpret_cast<const uint4*>(s_geo[h][d].off1);
-      const uint32_t f0[kNY] = {o0.x, o0.y, o0.z}, f1[kNY] = {o1.x, o1.y, o1.z};
       const __nv_bfloat16* __restrict__ pd = pv + static_cast<uint32_t>(i) * kN0L;
       const bool two = s_wy[h][d][0][3] != 0.f;                   // uniform over the CTA
-#pragma unroll
-      for (int k = 0; k < kNY; ++k) {
-        if (k < 2 || !two) {
-          r0[k] = __ldg(reinterpret_cast<const uint2*>(pd + f0[k]));
-          r1[k] = __ldg(reinterpret_cast<const uint2*>(pd + f1[k]));
-        }
+      r0[0] = __ldg(reinterpret_cast<const uint2*>(pd + o0.x));
+      r1[0] = __ldg(reinterpret_cast<const uint2*>(pd + o1.x));
+      r0[1] = __ldg(reinterpret_cast<const uint2*>(pd + o0.y));
+      r1[1] = __ldg(reinterpret_cast<const uint2*>(pd + o1.y));
+      if (!two) {
+        r0[2] = __ldg(reinterpret_cast<const uint2*>(pd + o0.z));
+        r1[2] = __ldg(reinterpret_cast<const uint2*>(pd + o1.z));
       }
     };
     auto work = [&](int i, int sq, const uint2 (&r0)[kNY], const uint2 (&r1)[kNY]) {
@@ -184,14 +186,14 @@ __global__ void __launch_bounds__(kLinesThreads, 2) hoist_lines_kernel(const Lin
       }
       if (sq >= 4) {                                                // last displacement of its class
         const int cls = sq - 4;
-        const size_t row = static_cast<size_t>(p.rowbase[h] + cls * R + i);
+        __nv_bfloat16* const grow = gline + (p.rowbase[h] + cls * R + i) * kN0L;   // this table row in line j = 0
 #pragma unroll
         for (int j = 0; j < LY; ++j)
           if (j >= jlo && j < jhi) {
             uint2 o;
             o.x = pack_bf16x2(acc[j][0].x, acc[j][0].y);
             o.y = pack_bf16x2(acc[j][1].x, acc[j][1].y);
-            *reinterpret_cast<uint2*>(p.G + (static_cast<size_t>(out_line0 + j) * p.rpl + row) * kN0L + v * 4) = o;
+            *reinterpret_cast<uint2*>(grow + j * line_stride) = o;
           }
       }
     };
